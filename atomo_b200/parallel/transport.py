@@ -1,0 +1,172 @@
+"""First-class communication layer (the reference has none: MPI calls are
+inlined at ~70 sites).
+
+:class:`Transport` is the protocol the PS / worker roles talk to:
+
+====================  =====================================================
+reference call site   Transport method
+====================  =====================================================
+C1 ``isend(step)``    ``send_step(step)``          (master:246-252)
+C2 ``irecv(tag 10)``  ``recv_step()``              (worker:267-273)
+C3/C4 ``Bcast``       ``bcast_params(flat)``       (master:270-279, worker:275-287)
+C7 ``isend(tag 88+i)````push(codes, step)``        (worker:330-335)
+C5/C6 ``irecv``/``waitany`` ``gather(step, need)`` (master:281-290, 198-214)
+C10 tag 77            ``send_kill(w)`` / ``kill_requested()``  (lenet.py:173-180)
+====================  =====================================================
+
+:class:`TorchDistTransport` implements it over ``torch.distributed`` — gloo on
+CPU (BASELINE config 1) or NCCL on GPUs (the *baseline* the fused NVLink path
+in ``atomo_b200.parallel.symm`` / ``runtime.engine`` is measured against).
+Differences from the reference: parameters travel as ONE flat fp32 broadcast
+(not P float64 Bcasts), a worker's step message is ONE packed buffer
+(``wire.pack``), and messages carry the step so stale gradients are dropped
+(the reference's ``generate_tag`` idea, resnet_split.py:25-39, made real).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import wire
+
+STOP_STEP = -1
+
+
+class Transport:
+    rank: int
+    world_size: int
+
+    @property
+    def num_workers(self) -> int:
+        return self.world_size - 1
+
+    def send_step(self, step: int) -> None: raise NotImplementedError
+    def recv_step(self) -> int: raise NotImplementedError
+    def bcast_params(self, flat: torch.Tensor) -> None: raise NotImplementedError
+    def push(self, codes: list, step: int) -> int: raise NotImplementedError
+    def gather(self, step: int, need: Optional[int] = None): raise NotImplementedError
+    def send_kill(self, worker_rank: int) -> None: raise NotImplementedError
+    def kill_requested(self) -> bool: return False
+    def barrier(self) -> None: raise NotImplementedError
+
+
+class TorchDistTransport(Transport):
+    """PS = rank 0, workers = ranks 1..W-1, over an initialized process group."""
+
+    def __init__(self, device: Optional[torch.device] = None, group=None, timeout_s: float = 300.0):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialized first")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+        self.device = device
+        self.timeout_s = timeout_s
+        self._stale_dropped = 0
+        self.bytes_sent = 0
+
+    # -- step handshake -------------------------------------------------
+    def send_step(self, step: int) -> None:
+        t = torch.tensor([step], dtype=torch.int64, device=self.device)
+        reqs = [dist.isend(t, dst=w, group=self.group, tag=10) for w in range(1, self.world_size)]
+        for r in reqs:
+            r.wait()
+
+    def recv_step(self) -> int:
+        t = torch.zeros(1, dtype=torch.int64, device=self.device)
+        dist.recv(t, src=0, group=self.group, tag=10)
+        return int(t.item())
+
+    # -- parameters -------------------------------------------------------
+    def bcast_params(self, flat: torch.Tensor) -> None:
+        dist.broadcast(flat, src=0, group=self.group)
+
+    # -- gradients: worker side ------------------------------------------
+    def push(self, codes: list, step: int) -> int:
+        buf = wire.pack({"step": step, "rank": self.rank, "codes": codes}, device=self.device)
+        n = torch.tensor([buf.numel(), step], dtype=torch.int64, device=self.device)
+        dist.send(n, dst=0, group=self.group, tag=87)
+        dist.send(buf, dst=0, group=self.group, tag=88)
+        self.bytes_sent += buf.numel()
+        return buf.numel()
+
+    # -- gradients: PS side ------------------------------------------------
+    def _recv_one(self, src):
+        """Receive one (header, payload) message; ``src=None`` = any source
+        (the reference's ``waitany``, master:198-214 — gloo only)."""
+        hdr = torch.zeros(2, dtype=torch.int64, device=self.device)
+        sender = dist.recv(hdr, src=src, group=self.group, tag=87)
+        sender = src if src is not None else sender
+        nbytes, msg_step = int(hdr[0].item()), int(hdr[1].item())
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        dist.recv(buf, src=sender, group=self.group, tag=88)
+        return sender, msg_step, buf
+
+    def gather(self, step: int, need: Optional[int] = None):
+        """Collect this step's messages.  Returns ``{worker_rank: codes}``.
+
+        ``need`` < num_workers gives backup-worker semantics (the reference's
+        ``--num-aggregate``, parsed at launcher:67 but never used): return as
+        soon as ``need`` workers have delivered (arrival order on gloo via
+        any-source receive; rank order on NCCL, which has no any-source).
+        Stragglers' messages carry an old step and are dropped when they
+        surface in a later call.  A dead worker surfaces as the process-group
+        timeout instead of the reference's infinite ``waitany`` block.
+        """
+        need = self.num_workers if need is None else min(need, self.num_workers)
+        got: Dict[int, list] = {}
+        any_source = self.backend == "gloo"
+        order = list(range(1, self.world_size))
+        if not any_source:
+            need = self.num_workers  # NCCL has no any-source receive: wait for everyone, rank order
+        cursor = 0
+        while len(got) < need:
+            if any_source:
+                sender, msg_step, buf = self._recv_one(None)
+            else:
+                sender, msg_step, buf = self._recv_one(order[cursor])
+                cursor += 1
+            if msg_step == step:
+                got[sender] = wire.unpack(buf)["codes"]
+            else:  # stale gradient from a straggler: drop
+                self._stale_dropped += 1
+        # workers that did not make the cut still owe us a (stale) message
+        return got
+
+    # -- straggler kill signal (tag 77) -------------------------------------
+    def send_kill(self, worker_rank: int, step: int = 0) -> None:
+        t = torch.tensor([step], dtype=torch.int64, device=self.device)
+        dist.send(t, dst=worker_rank, group=self.group, tag=77)
+
+    def _kill_listener(self):
+        buf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        while True:
+            try:
+                dist.recv(buf, src=0, group=self.group, tag=77)
+            except Exception:
+                return
+            self._kill_flag.set()
+
+    def enable_kill_listener(self) -> None:
+        """Worker side: start a daemon thread blocking on tag 77 (the reference
+        polls ``Iprobe`` between layer backwards, lenet.py:173-180)."""
+        import threading
+        if getattr(self, "_kill_thread", None) is None:
+            self._kill_flag = threading.Event()
+            self._kill_thread = threading.Thread(target=self._kill_listener, daemon=True)
+            self._kill_thread.start()
+
+    def kill_requested(self) -> bool:
+        flag = getattr(self, "_kill_flag", None)
+        if flag is not None and flag.is_set():
+            flag.clear()
+            return True
+        return False
+
+    def barrier(self) -> None:
+        dist.barrier(group=self.group)

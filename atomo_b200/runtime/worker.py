@@ -1,0 +1,165 @@
+"""Worker role.
+
+Parity: ``DistributedWorker`` (``/root/reference/src/distributed_worker.py:98-370``):
+``__init__(comm, **kwargs)``, ``build_model(num_classes)``,
+``train(train_loader, test_loader)``; per step: fetch step -> fetch weights ->
+forward/backward -> encode every parameter's gradient -> push -> log line
+(``worker:255-258``, the format ``tiny_tuning_parser`` greps) -> periodic test
+evaluation (``worker:344-370``).  BN running statistics stay private to each
+worker like the reference (``worker:301-302``).
+
+Fixes: the CPU path encodes the real gradient (the reference's never assigns
+it, worker:319-323); the whole step's codes travel as one message.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..models import build_model
+from ..parallel.transport import Transport, STOP_STEP
+from ..utils import checkpoint as ckpt
+from ..utils.logging import worker_line, test_line
+from .flat import FlatLayout, bind_parameters
+from .master import STEP_START_, build_coder
+from .nn_ops import NN_Trainer, accuracy
+from ..codings import Coding
+
+
+class DistributedWorker(NN_Trainer):
+    def __init__(self, comm: Transport, **kwargs):
+        self.comm = comm
+        self.world_size = comm.world_size
+        self.rank = comm.rank
+        self.cur_step = 0
+        self.next_step = 0
+        self.batch_size = kwargs.get("batch_size", 128)
+        self.max_epochs = kwargs.get("max_epochs", 100)
+        self.momentum = kwargs.get("momentum", 0.5)
+        self.lr = kwargs.get("learning_rate", 0.01)
+        self.network_config = kwargs["network"]
+        self.dataset = kwargs.get("dataset", "")
+        self._max_steps = kwargs.get("max_steps", 10000)
+        self.comm_type = kwargs.get("comm_method", "Bcast")
+        self._compress = kwargs.get("compress", False)
+        self._enable_gpu = bool(kwargs.get("enable_gpu", False)) and torch.cuda.is_available()
+        self._eval_batch_size = 100
+        self._eval_freq = kwargs.get("eval_freq", 50)
+        self._train_dir = kwargs.get("train_dir", "output/models/")
+        self._svd_rank = kwargs.get("svd_rank", 0)
+        self._quantization_level = kwargs.get("quantization_level", 4)
+        self._bucket_size = kwargs.get("bucket_size", 512)
+        self._code = kwargs.get("code", "sgd")
+        self._eval_batches = kwargs.get("eval_batches", None)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self._enable_gpu else torch.device("cpu")
+        self._coder = build_coder(kwargs, worker_side=True)
+        self.last_stats = {}
+
+    def build_model(self, num_classes: int = 10):
+        self.network = build_model(self.network_config, num_classes, self.dataset).to(self.device)
+        self.layout = FlatLayout.from_module(self.network)
+        # the receive buffer IS the parameter storage (parity role: ModelBuffer, worker:84-95)
+        self.flat_params = torch.zeros(self.layout.total, dtype=torch.float32, device=self.device)
+        bind_parameters(self.network, self.flat_params, self.layout)
+        self.optimizer = torch.optim.SGD(self.network.parameters(), lr=self.lr, momentum=self.momentum)
+        self.criterion = nn.CrossEntropyLoss()
+        return self
+
+    # ------------------------------------------------------------------
+    def train(self, train_loader, test_loader=None):
+        n_data = len(train_loader.dataset)
+        print("Worker {}: starting training".format(self.rank))
+        iter_start = time.time()
+        for num_epoch in range(self.max_epochs):
+            for batch_idx, (x, y) in enumerate(train_loader):
+                self.next_step = self.async_fetch_step()
+                if self.next_step == STOP_STEP:
+                    return
+                self.update_step()
+                if num_epoch == 0 and batch_idx == 0:
+                    assert self.cur_step >= STEP_START_
+                iter_start = time.time()
+                x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+
+                t0 = time.time()
+                self.async_fetch_weights_bcast()
+                fetch_weight_duration = time.time() - t0
+
+                self.network.train()
+                self.optimizer.zero_grad()
+                comp_start = time.time()
+                logits = self.network(x)
+                loss = self.criterion(logits, y)
+                loss.backward()
+                comp_dur = time.time() - comp_start
+
+                encode_start = time.time()
+                msgs, msg_bytes = self._encode()
+                encode_dur = time.time() - encode_start
+
+                comm_start = time.time()
+                self._send_grads(msgs)
+                comm_dur = time.time() - comm_start
+
+                prec1, prec5 = accuracy(logits.detach(), y, topk=(1, 5))
+                self.last_stats = dict(step=self.cur_step, loss=float(loss.item()), prec1=float(prec1.item()),
+                                       prec5=float(prec5.item()), msg_bytes=msg_bytes, fetch=fetch_weight_duration)
+                print(worker_line(self.rank, self.cur_step, num_epoch, batch_idx * self.batch_size, n_data,
+                                  loss.item(), time.time() - iter_start, comp_dur, encode_dur, comm_dur,
+                                  msg_bytes / (1024.0 ** 2), prec1.item(), prec5.item()))
+                if test_loader is not None and self.cur_step % self._eval_freq == 0:
+                    self._evaluate_model(test_loader)
+        # epochs exhausted before the PS stopped: keep answering until STOP
+        while self.async_fetch_step() != STOP_STEP:
+            self.async_fetch_weights_bcast()
+            self._send_grads([self._coder.encode(torch.zeros_like(p)) for p in self.network.parameters()])
+
+    def async_fetch_step(self) -> int:
+        return self.comm.recv_step()
+
+    sync_fetch_step = async_fetch_step
+
+    def update_step(self) -> bool:
+        changed = self.cur_step != self.next_step
+        self.cur_step = self.next_step
+        return changed
+
+    def async_fetch_weights_bcast(self):
+        self.comm.bcast_params(self.flat_params)
+
+    def _encode(self):
+        msgs, nbytes = [], 0
+        for p in self.network.parameters():
+            coded = self._coder.encode(p.grad.detach().to(torch.float32))
+            nbytes += Coding.wire_bytes(coded)
+            msgs.append(coded)
+        return msgs, nbytes
+
+    def _send_grads(self, msgs):
+        self.comm.push(msgs, self.cur_step)
+
+    def _generate_model_path(self):
+        return ckpt.model_path(self._train_dir, self.cur_step)
+
+    def _save_model(self, file_path=None):
+        ckpt.save_model(self._train_dir, self.cur_step, self.network)
+
+    @torch.no_grad()
+    def _evaluate_model(self, test_loader):
+        self.network.eval()
+        test_loss, p1, p5, nb, n = 0.0, 0.0, 0.0, 0, 0
+        for i, (data, target) in enumerate(test_loader):
+            if self._eval_batches is not None and i >= self._eval_batches:
+                break
+            data, target = data.to(self.device), target.to(self.device)
+            output = self.network(data)
+            test_loss += F.cross_entropy(output, target, reduction="sum").item()
+            a1, a5 = accuracy(output, target, topk=(1, 5))
+            p1 += a1.item(); p5 += a5.item(); nb += 1; n += len(target)
+        nb = max(nb, 1)
+        print(test_line(self.cur_step, test_loss / max(n, 1), p1 / nb, p5 / nb))
+        self.network.train()
+        return {"loss": test_loss / max(n, 1), "prec1": p1 / nb, "prec5": p5 / nb}

@@ -1,0 +1,65 @@
+"""Launcher flag surface (parity: ``add_fit_args``,
+``/root/reference/src/distributed_nn.py:31-82`` — every flag of SURVEY.md 2.7 is
+kept with its default) plus the B200-specific additions."""
+from __future__ import annotations
+
+import argparse
+
+
+def bool_flag(v) -> bool:
+    """The reference declares ``type=bool`` (any non-empty string is True and
+    the scripts pass ``--enable-gpu=`` for False).  This keeps that contract
+    and additionally understands 0/false/no."""
+    if isinstance(v, bool):
+        return v
+    return str(v).strip().lower() not in ("", "0", "false", "no", "off", "none")
+
+
+def add_fit_args(parser: argparse.ArgumentParser, argv=None):
+    p = parser
+    p.add_argument("--batch-size", type=int, default=128, metavar="N")
+    p.add_argument("--test-batch-size", type=int, default=1000, metavar="N")
+    p.add_argument("--max-steps", type=int, default=10000, metavar="N")
+    p.add_argument("--epochs", type=int, default=100, metavar="N")
+    p.add_argument("--lr", type=float, default=0.01, metavar="LR")
+    p.add_argument("--momentum", type=float, default=0.5, metavar="M")
+    p.add_argument("--lr-shrinkage", type=float, default=0.95, metavar="M")
+    p.add_argument("--no-cuda", action="store_true", default=False)
+    p.add_argument("--seed", type=int, default=1, metavar="S")
+    p.add_argument("--log-interval", type=int, default=10, metavar="N")
+    p.add_argument("--network", type=str, default="LeNet", metavar="N")
+    p.add_argument("--code", type=str, default="sgd",
+                   help="sgd | svd | qsgd | terngrad | entrywise | qsvd")
+    p.add_argument("--bucket-size", type=int, default=512)
+    p.add_argument("--dataset", type=str, default="MNIST", metavar="N")
+    p.add_argument("--comm-type", type=str, default="Bcast", metavar="N")
+    p.add_argument("--num-aggregate", type=int, default=0, metavar="N",
+                   help="gradients to wait for per step (0 = all workers; reference default 5 was a no-op)")
+    p.add_argument("--eval-freq", type=int, default=50, metavar="N")
+    p.add_argument("--train-dir", type=str, default="output/models/", metavar="N")
+    p.add_argument("--compress", type=bool_flag, default=False)
+    p.add_argument("--enable-gpu", type=bool_flag, default=False)
+    p.add_argument("--svd-rank", type=int, default=0)
+    p.add_argument("--quantization-level", type=int, default=4)
+    # ---- additions -----------------------------------------------------
+    p.add_argument("--backend", type=str, default="auto", choices=["auto", "gloo", "nccl", "p2p"],
+                   help="gloo (CPU), nccl (baseline), p2p (fused NVLink peer-memory engine)")
+    p.add_argument("--nproc", type=int, default=0, help="spawn this many local ranks (0 = use torchrun env)")
+    p.add_argument("--synthetic", type=bool_flag, default=None, help="force synthetic data (default: auto)")
+    p.add_argument("--data-root", type=str, default=".")
+    p.add_argument("--train-len", type=int, default=0, help="truncate the training set (0 = full)")
+    p.add_argument("--test-len", type=int, default=0)
+    p.add_argument("--entry-budget", type=float, default=0.05, help="entry-wise ATOMO budget (fraction or count)")
+    p.add_argument("--sampling", type=str, default="bernoulli", choices=["bernoulli", "systematic"])
+    p.add_argument("--prob-rule", type=str, default="reference", choices=["reference", "waterfill"])
+    p.add_argument("--optimizer", type=str, default="sgd", choices=["sgd", "adam"])
+    p.add_argument("--weight-decay", type=float, default=0.0)
+    p.add_argument("--nesterov", type=bool_flag, default=False)
+    p.add_argument("--resume", type=bool_flag, default=False)
+    p.add_argument("--dtype", type=str, default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--ps-mode", type=str, default="colocated", choices=["colocated", "dedicated"],
+                   help="p2p backend: rank 0 hosts the PS and (colocated) also trains")
+    p.add_argument("--master-addr", type=str, default="127.0.0.1")
+    p.add_argument("--master-port", type=int, default=29511)
+    p.add_argument("--eval-batches", type=int, default=0, help="cap test batches per evaluation (0 = all)")
+    return p.parse_args(argv)
