@@ -1,0 +1,276 @@
+// Python bindings for the atomo_b200 native runtime (torch extension `atomo_b200._C`).
+// Kernels live in the .cu files behind a plain C ABI; this file only adapts
+// torch tensors / raw peer pointers to those launchers on the current stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <cstdint>
+#include <string>
+
+extern "C" {
+// symm_heap.cpp
+const char* atomo_heap_last_error();
+int atomo_heap_multicast_supported(int device);
+int atomo_heap_posix_fd_supported(int device);
+void* atomo_heap_create_vmm(int rank, int world, int device, size_t bytes, const char* job, int want_mc,
+                            double timeout_s);
+int atomo_heap_mc_phase_a(void* h, double timeout_s);
+int atomo_heap_mc_phase_b(void* h);
+void* atomo_heap_create_ipc(int rank, int world, int device, size_t bytes, unsigned char* handle_out64);
+int atomo_heap_open_ipc(void* h, const unsigned char* all_handles);
+uint64_t atomo_heap_ptr(void* h, int rank);
+uint64_t atomo_heap_mc_ptr(void* h);
+uint64_t atomo_heap_bytes(void* h);
+const char* atomo_heap_mode(void* h);
+void atomo_heap_destroy(void* h);
+// svd_kernels.cu
+void atomo_launch_gram(const float* grad, const void* layers, const void* tiles, int ntiles, float* gpart,
+                       cudaStream_t stream);
+void atomo_launch_eig_sample(const void* layers, const int* ts_layers, int n_ts, const float* gpart, float* vsel,
+                             int* selcount, float* sigma_out, float* ps_arena_peer, long long arena_floats,
+                             const void* ctrl, const float* ext_uniforms, int rank, int random_sample,
+                             int waterfill, int systematic, int worker_index, cudaStream_t stream);
+void atomo_launch_project_push(const float* grad, const void* layers, const void* tiles, int ntiles,
+                               const float* vsel, const int* selcount, float* ps_arena_peer,
+                               long long arena_floats, int* push_flag_peer, void* ctrl, int worker_index,
+                               int signal, cudaStream_t stream);
+void atomo_launch_signal_push(int* push_flag_peer, const void* ctrl, int worker_index, cudaStream_t stream);
+// ps_kernels.cu
+int atomo_ps_smem_bytes();
+int atomo_ps_tile_elems();
+int atomo_ps_max_rows();
+int atomo_ps_dense_elems();
+int atomo_ps_max_workers();
+void atomo_launch_ps_update(const void* layers, const void* tiles, int ntiles, int W, int nflags, int nranks,
+                            float* params, float* momentum, float* const* params_peer, float* params_mc,
+                            const float* const* grads_peer, const float* grads_mc, const float* arenas,
+                            long long arena_floats, int* push_flags, int* const* param_flag_peer, void* ctrl,
+                            long long timeout_ticks, float inv_w, int grid, cudaStream_t stream);
+void atomo_launch_wait_params(const int* param_flag, void* ctrl, long long timeout_ticks, cudaStream_t stream);
+void atomo_launch_advance_step(void* ctrl, cudaStream_t stream);
+void atomo_launch_param_bcast(const float* src, float* const* params_peer, float* params_mc, int nranks,
+                              int self_rank, long long numel, cudaStream_t stream);
+void atomo_launch_set_flags(int* const* flag_peer, int nranks, int value, cudaStream_t stream);
+// qsgd_kernels.cu / entrywise_kernels.cu
+void atomo_launch_qsgd_encode(const float* grad, long long numel, int bucket, int q, int terngrad,
+                              const float* clip_ptr, unsigned long long* words_out, float* norms_out,
+                              const void* ctrl, int worker_index, const float* ext_uniforms, cudaStream_t stream);
+void atomo_launch_qsgd_decode_sum(const unsigned long long* const* words, const float* const* norms, int W,
+                                  long long numel, int bucket, int q, int terngrad, float* out_sum,
+                                  const int* push_flags, void* ctrl, long long timeout_ticks, cudaStream_t stream);
+int atomo_qsgd_max_bucket();
+void atomo_launch_entrywise_encode(const float* grad, const void* layers, const void* tiles, int ntiles, float* l1,
+                                   int nlayers, float budget, int* idx_out, float* val_out, int* count_out,
+                                   int capacity, int* local_count, int* push_flag_peer, void* ctrl,
+                                   int worker_index, const float* ext_uniforms, int signal, cudaStream_t stream);
+void atomo_launch_entrywise_scatter(const int* const* idx, const float* const* val, const int* const* count, int W,
+                                    int capacity, float* out_sum, long long numel, const int* push_flags,
+                                    void* ctrl, long long timeout_ticks, cudaStream_t stream);
+}
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+template <typename T>
+inline T* P(uint64_t v) { return reinterpret_cast<T*>(static_cast<uintptr_t>(v)); }
+inline const float* fptr(const torch::Tensor& t) { return t.defined() && t.numel() ? t.data_ptr<float>() : nullptr; }
+
+void check_cuda_f32(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == torch::kFloat32, name, " must be float32");
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+}
+
+// ---------------------------------------------------------------------------------------------- heap
+struct Heap {
+  void* h = nullptr;
+  ~Heap() { if (h) atomo_heap_destroy(h); }
+};
+
+uint64_t heap_create_vmm(int rank, int world, int device, uint64_t bytes, const std::string& job, bool want_mc,
+                         double timeout_s) {
+  void* h = atomo_heap_create_vmm(rank, world, device, bytes, job.c_str(), want_mc ? 1 : 0, timeout_s);
+  return reinterpret_cast<uint64_t>(h);
+}
+py::tuple heap_create_ipc(int rank, int world, int device, uint64_t bytes) {
+  unsigned char handle[64] = {0};
+  void* h = atomo_heap_create_ipc(rank, world, device, bytes, handle);
+  return py::make_tuple(reinterpret_cast<uint64_t>(h), py::bytes(reinterpret_cast<const char*>(handle), 64));
+}
+bool heap_open_ipc(uint64_t h, const std::string& all_handles) {
+  return atomo_heap_open_ipc(P<void>(h), reinterpret_cast<const unsigned char*>(all_handles.data())) != 0;
+}
+
+torch::Tensor tensor_from_ptr(uint64_t ptr, int64_t numel, const std::string& dtype, int device) {
+  auto dt = dtype == "int32" ? torch::kInt32 : dtype == "int64" ? torch::kInt64 : dtype == "uint8" ? torch::kUInt8
+                                                                                                   : torch::kFloat32;
+  auto opts = torch::TensorOptions().dtype(dt).device(torch::kCUDA, device);
+  return torch::from_blob(P<void>(ptr), {numel}, [](void*) {}, opts);
+}
+
+// ---------------------------------------------------------------------------------------------- svd encode
+void gram(const torch::Tensor& grad, const torch::Tensor& layers, const torch::Tensor& tiles, int ntiles,
+          torch::Tensor gpart) {
+  check_cuda_f32(grad, "grad");
+  c10::cuda::CUDAGuard guard(grad.device());
+  atomo_launch_gram(grad.data_ptr<float>(), layers.data_ptr(), tiles.data_ptr(), ntiles, gpart.data_ptr<float>(),
+                    cur_stream());
+}
+
+void eig_sample(const torch::Tensor& layers, const torch::Tensor& ts_layers, const torch::Tensor& gpart,
+                torch::Tensor vsel, torch::Tensor selcount, c10::optional<torch::Tensor> sigma_out,
+                uint64_t ps_arena_peer, int64_t arena_floats, const torch::Tensor& ctrl,
+                c10::optional<torch::Tensor> ext_uniforms, int rank, bool random_sample, bool waterfill,
+                bool systematic, int worker_index) {
+  c10::cuda::CUDAGuard guard(gpart.device());
+  atomo_launch_eig_sample(layers.data_ptr(), ts_layers.data_ptr<int>(), (int)ts_layers.numel(),
+                          gpart.data_ptr<float>(), vsel.data_ptr<float>(), selcount.data_ptr<int>(),
+                          sigma_out.has_value() ? sigma_out->data_ptr<float>() : nullptr, P<float>(ps_arena_peer),
+                          arena_floats, ctrl.data_ptr(),
+                          ext_uniforms.has_value() ? ext_uniforms->data_ptr<float>() : nullptr, rank,
+                          random_sample, waterfill, systematic, worker_index, cur_stream());
+}
+
+void project_push(const torch::Tensor& grad, const torch::Tensor& layers, const torch::Tensor& tiles, int ntiles,
+                  const torch::Tensor& vsel, const torch::Tensor& selcount, uint64_t ps_arena_peer,
+                  int64_t arena_floats, uint64_t push_flag_peer, torch::Tensor ctrl, int worker_index, bool signal) {
+  check_cuda_f32(grad, "grad");
+  c10::cuda::CUDAGuard guard(grad.device());
+  atomo_launch_project_push(grad.data_ptr<float>(), layers.data_ptr(), tiles.data_ptr(), ntiles,
+                            vsel.data_ptr<float>(), selcount.data_ptr<int>(), P<float>(ps_arena_peer), arena_floats,
+                            P<int>(push_flag_peer), ctrl.data_ptr(), worker_index, signal ? 1 : 0, cur_stream());
+}
+
+void signal_push(uint64_t push_flag_peer, const torch::Tensor& ctrl, int worker_index) {
+  c10::cuda::CUDAGuard guard(ctrl.device());
+  atomo_launch_signal_push(P<int>(push_flag_peer), ctrl.data_ptr(), worker_index, cur_stream());
+}
+
+// ---------------------------------------------------------------------------------------------- PS
+void ps_update(const torch::Tensor& layers, const torch::Tensor& tiles, int ntiles, int W, int nflags, int nranks,
+               torch::Tensor params, torch::Tensor momentum, const torch::Tensor& params_peer, uint64_t params_mc,
+               const torch::Tensor& grads_peer, uint64_t grads_mc, uint64_t arenas, int64_t arena_floats,
+               uint64_t push_flags, const torch::Tensor& param_flag_peer, torch::Tensor ctrl,
+               int64_t timeout_ticks, double inv_w, int grid) {
+  check_cuda_f32(params, "params");
+  check_cuda_f32(momentum, "momentum");
+  TORCH_CHECK(W <= atomo_ps_max_workers(), "too many workers for ps_update");
+  c10::cuda::CUDAGuard guard(params.device());
+  atomo_launch_ps_update(layers.data_ptr(), tiles.data_ptr(), ntiles, W, nflags, nranks, params.data_ptr<float>(),
+                         momentum.data_ptr<float>(), reinterpret_cast<float* const*>(params_peer.data_ptr()),
+                         P<float>(params_mc), reinterpret_cast<const float* const*>(grads_peer.data_ptr()),
+                         P<const float>(grads_mc), P<const float>(arenas), arena_floats, P<int>(push_flags),
+                         reinterpret_cast<int* const*>(param_flag_peer.data_ptr()), ctrl.data_ptr(), timeout_ticks,
+                         (float)inv_w, grid, cur_stream());
+}
+
+void wait_params(uint64_t param_flag, torch::Tensor ctrl, int64_t timeout_ticks) {
+  c10::cuda::CUDAGuard guard(ctrl.device());
+  atomo_launch_wait_params(P<const int>(param_flag), ctrl.data_ptr(), timeout_ticks, cur_stream());
+}
+void advance_step(torch::Tensor ctrl) {
+  c10::cuda::CUDAGuard guard(ctrl.device());
+  atomo_launch_advance_step(ctrl.data_ptr(), cur_stream());
+}
+void param_bcast(const torch::Tensor& src, const torch::Tensor& params_peer, uint64_t params_mc, int nranks,
+                 int self_rank, int64_t numel) {
+  check_cuda_f32(src, "src");
+  c10::cuda::CUDAGuard guard(src.device());
+  atomo_launch_param_bcast(src.data_ptr<float>(), reinterpret_cast<float* const*>(params_peer.data_ptr()),
+                           P<float>(params_mc), nranks, self_rank, numel, cur_stream());
+}
+void set_flags(const torch::Tensor& flag_peer, int nranks, int value) {
+  c10::cuda::CUDAGuard guard(flag_peer.device());
+  atomo_launch_set_flags(reinterpret_cast<int* const*>(flag_peer.data_ptr()), nranks, value, cur_stream());
+}
+
+// ---------------------------------------------------------------------------------------------- qsgd / entrywise
+void qsgd_encode(const torch::Tensor& grad, int64_t numel, int bucket, int q, bool terngrad,
+                 c10::optional<torch::Tensor> clip, uint64_t words_out, uint64_t norms_out,
+                 const torch::Tensor& ctrl, int worker_index, c10::optional<torch::Tensor> ext_uniforms) {
+  check_cuda_f32(grad, "grad");
+  TORCH_CHECK(q >= 1 && q <= 14, "GPU QSGD supports quantization_level in [1, 14]");
+  TORCH_CHECK(bucket >= 32 && bucket <= atomo_qsgd_max_bucket(), "bucket_size out of range for the GPU path");
+  c10::cuda::CUDAGuard guard(grad.device());
+  atomo_launch_qsgd_encode(grad.data_ptr<float>(), numel, bucket, q, terngrad,
+                           clip.has_value() ? clip->data_ptr<float>() : nullptr, P<unsigned long long>(words_out),
+                           P<float>(norms_out), ctrl.data_ptr(), worker_index,
+                           ext_uniforms.has_value() ? ext_uniforms->data_ptr<float>() : nullptr, cur_stream());
+}
+void qsgd_decode_sum(const torch::Tensor& words_ptrs, const torch::Tensor& norms_ptrs, int W, int64_t numel,
+                     int bucket, int q, bool terngrad, torch::Tensor out_sum, uint64_t push_flags,
+                     torch::Tensor ctrl, int64_t timeout_ticks) {
+  check_cuda_f32(out_sum, "out_sum");
+  c10::cuda::CUDAGuard guard(out_sum.device());
+  atomo_launch_qsgd_decode_sum(reinterpret_cast<const unsigned long long* const*>(words_ptrs.data_ptr()),
+                               reinterpret_cast<const float* const*>(norms_ptrs.data_ptr()), W, numel, bucket, q,
+                               terngrad, out_sum.data_ptr<float>(), P<const int>(push_flags), ctrl.data_ptr(),
+                               timeout_ticks, cur_stream());
+}
+void entrywise_encode(const torch::Tensor& grad, const torch::Tensor& layers, const torch::Tensor& tiles,
+                      int ntiles, torch::Tensor l1, double budget, uint64_t idx_out, uint64_t val_out,
+                      uint64_t count_out, int capacity, torch::Tensor local_count, uint64_t push_flag_peer,
+                      torch::Tensor ctrl, int worker_index, c10::optional<torch::Tensor> ext_uniforms, bool signal) {
+  check_cuda_f32(grad, "grad");
+  c10::cuda::CUDAGuard guard(grad.device());
+  atomo_launch_entrywise_encode(grad.data_ptr<float>(), layers.data_ptr(), tiles.data_ptr(), ntiles,
+                                l1.data_ptr<float>(), (int)l1.numel(), (float)budget, P<int>(idx_out),
+                                P<float>(val_out), P<int>(count_out), capacity, local_count.data_ptr<int>(),
+                                P<int>(push_flag_peer), ctrl.data_ptr(), worker_index,
+                                ext_uniforms.has_value() ? ext_uniforms->data_ptr<float>() : nullptr,
+                                signal ? 1 : 0, cur_stream());
+}
+void entrywise_scatter(const torch::Tensor& idx_ptrs, const torch::Tensor& val_ptrs, const torch::Tensor& count_ptrs,
+                       int W, int capacity, torch::Tensor out_sum, int64_t numel, uint64_t push_flags,
+                       torch::Tensor ctrl, int64_t timeout_ticks) {
+  check_cuda_f32(out_sum, "out_sum");
+  c10::cuda::CUDAGuard guard(out_sum.device());
+  atomo_launch_entrywise_scatter(reinterpret_cast<const int* const*>(idx_ptrs.data_ptr()),
+                                 reinterpret_cast<const float* const*>(val_ptrs.data_ptr()),
+                                 reinterpret_cast<const int* const*>(count_ptrs.data_ptr()), W, capacity,
+                                 out_sum.data_ptr<float>(), numel, P<const int>(push_flags), ctrl.data_ptr(),
+                                 timeout_ticks, cur_stream());
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "atomo_b200 native runtime: symmetric NVLink heap + sm_100a gradient-coding kernels";
+  // heap
+  m.def("heap_last_error", []() { return std::string(atomo_heap_last_error()); });
+  m.def("heap_multicast_supported", &atomo_heap_multicast_supported);
+  m.def("heap_posix_fd_supported", &atomo_heap_posix_fd_supported);
+  m.def("heap_create_vmm", &heap_create_vmm);
+  m.def("heap_mc_phase_a", [](uint64_t h, double t) { return atomo_heap_mc_phase_a(P<void>(h), t) != 0; });
+  m.def("heap_mc_phase_b", [](uint64_t h) { return atomo_heap_mc_phase_b(P<void>(h)) != 0; });
+  m.def("heap_create_ipc", &heap_create_ipc);
+  m.def("heap_open_ipc", &heap_open_ipc);
+  m.def("heap_ptr", [](uint64_t h, int r) { return atomo_heap_ptr(P<void>(h), r); });
+  m.def("heap_mc_ptr", [](uint64_t h) { return atomo_heap_mc_ptr(P<void>(h)); });
+  m.def("heap_bytes", [](uint64_t h) { return atomo_heap_bytes(P<void>(h)); });
+  m.def("heap_mode", [](uint64_t h) { return std::string(atomo_heap_mode(P<void>(h))); });
+  m.def("heap_destroy", [](uint64_t h) { atomo_heap_destroy(P<void>(h)); });
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  // kernels
+  m.def("gram", &gram);
+  m.def("eig_sample", &eig_sample);
+  m.def("project_push", &project_push);
+  m.def("signal_push", &signal_push);
+  m.def("ps_update", &ps_update);
+  m.def("wait_params", &wait_params);
+  m.def("advance_step", &advance_step);
+  m.def("param_bcast", &param_bcast);
+  m.def("set_flags", &set_flags);
+  m.def("qsgd_encode", &qsgd_encode);
+  m.def("qsgd_decode_sum", &qsgd_decode_sum);
+  m.def("entrywise_encode", &entrywise_encode);
+  m.def("entrywise_scatter", &entrywise_scatter);
+  // constants
+  m.def("ps_smem_bytes", &atomo_ps_smem_bytes);
+  m.def("ps_tile_elems", &atomo_ps_tile_elems);
+  m.def("ps_max_rows", &atomo_ps_max_rows);
+  m.def("ps_dense_elems", &atomo_ps_dense_elems);
+  m.def("ps_max_workers", &atomo_ps_max_workers);
+  m.def("qsgd_max_bucket", &atomo_qsgd_max_bucket);
+}

@@ -1,0 +1,448 @@
+"""Fused B200 engine: the whole PS training step on NVLink peer memory.
+
+Where the reference runs ``Bcast(float64) x P -> fwd/bwd ->
+host SVD x P -> pickle -> isend x P -> waitany -> np.dot decode -> SGD`` with
+every tensor staged through host numpy, this engine keeps everything on the
+GPUs and issues, per step and per rank, a fixed sequence of kernels that can be
+captured in ONE CUDA graph:
+
+  wait_params (spin on the step flag the PS wrote into our HBM)        [K9]
+  -> forward / backward (PyTorch, parameters and gradients are views into
+     flat buffers that live in the symmetric heap)
+  -> encode + push: gram / eig_sample / project_push  (or qsgd / entry-wise);
+     factors are stored straight into rank 0's arena through NVLink     [K1/K3/K5]
+  -> rank 0 only: ps_update — wait for W push flags, low-rank reconstruct or
+     NVLS in-switch dense reduce, momentum-SGD, multicast the new
+     parameters to every rank, raise the step flags                     [K2/K7/K8]
+  -> advance the device-side step counter.
+
+Cross-GPU ordering is carried entirely by step-stamped flags in peer memory, so
+no host synchronisation, NCCL call or MPI-style handshake sits on the path.
+Rank 0 hosts the PS and (``ps_mode='colocated'``, default) also trains; with
+``ps_mode='dedicated'`` it only serves, like the reference's rank 0.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..ops import plan as P
+from ..ops._ext import load as load_ext
+from ..parallel.symm import SymmetricHeap
+from .flat import bind_gradients, bind_parameters, FlatLayout
+
+SIGNAL_INTS = 1024
+PARAM_FLAG_SLOT = 64  # index of the param flag inside the signal region
+
+
+def _dev_bytes(b: bytes, device) -> torch.Tensor:
+    t = torch.frombuffer(bytearray(b if len(b) else b"\0" * 16), dtype=torch.uint8)
+    return t.to(device)
+
+
+class FusedEngine:
+    def __init__(self, model: nn.Module, rank: int = 0, world: int = 1, code: str = "svd", svd_rank: int = 3,
+                 lr: float = 0.01, momentum: float = 0.0, weight_decay: float = 0.0, nesterov: bool = False,
+                 dampening: float = 0.0, ps_mode: str = "colocated", sampling: str = "bernoulli",
+                 prob_rule: str = "reference", random_sample: bool = True, seed: int = 1,
+                 quantization_level: int = 4, bucket_size: int = 512, entry_budget: float = 0.05,
+                 dtype: str = "fp32", channels_last: bool = False, use_graph: bool = True, group=None,
+                 multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
+                 criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None):
+        self.C = load_ext()
+        self.rank, self.world, self.group = rank, world, group
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.code = code.lower()
+        if self.code in ("dense", "lossless"):
+            self.code = "sgd"
+        self.svd_rank = int(svd_rank)
+        self.ps_mode = ps_mode if world > 1 else "colocated"
+        self.first_worker = 0 if self.ps_mode == "colocated" else 1
+        self.W = world - self.first_worker
+        self.is_ps = rank == 0
+        self.is_worker = rank >= self.first_worker
+        self.worker_index = rank - self.first_worker
+        self.systematic = sampling == "systematic"
+        self.waterfill = prob_rule == "waterfill"
+        self.random_sample = random_sample
+        self.q, self.bucket = int(quantization_level), int(bucket_size)
+        self.entry_budget = float(entry_budget)
+        self.autocast = dtype == "bf16"
+        self.channels_last = channels_last
+        self.use_graph = use_graph
+        self.criterion = criterion or nn.CrossEntropyLoss()
+        self.timeout_ticks = int(timeout_s * 1.5e9)
+        self.step = 1
+        self.lr = lr
+        self.model = model.to(self.device)
+        self.launches_per_step = 0
+
+        # ---- plan + symmetric heap -----------------------------------------------------------
+        self.layout = FlatLayout.from_module(self.model)
+        shapes = self.layout.shapes
+        plan_code = self.code if self.code == "svd" else "sgd"
+        self.plan = P.build_plan(shapes, plan_code, self.svd_rank, self.systematic, offsets=self.layout.offsets)
+        assert self.plan.total_elems == self.layout.total
+        total = self.plan.total_elems
+        nb = (total + self.bucket - 1) // self.bucket
+        E = 64 // (2 + self.q)
+        self.q_words = (self.bucket + E - 1) // E
+        exp_atoms = self._entry_expected(total)
+        self.ew_capacity = int(exp_atoms * 1.25) + 4096
+        need = 4 * SIGNAL_INTS + 2 * 4 * total + 4096
+        if self.code == "svd":
+            need += 4 * self.plan.arena_floats * self.W
+        elif self.code in ("qsgd", "terngrad"):
+            need += self.W * (8 * nb * self.q_words + 4 * nb + 512)
+        elif self.code == "entrywise":
+            need += self.W * (8 * self.ew_capacity + 1024)
+        self.heap = SymmetricHeap(need + (1 << 20), rank, world, self.device.index, group=group,
+                                  multicast=multicast, mode=heap_mode)
+        h = self.heap
+        h.alloc("signals", 4 * SIGNAL_INTS)
+        h.alloc("params", 4 * total)
+        h.alloc("grads", 4 * total)
+        if self.code == "svd":
+            h.alloc("arena", 4 * self.plan.arena_floats * self.W)
+        elif self.code in ("qsgd", "terngrad"):
+            h.alloc("qwords", 8 * nb * self.q_words * self.W)
+            h.alloc("qnorms", 4 * nb * self.W)
+        elif self.code == "entrywise":
+            h.alloc("ew_idx", 4 * self.ew_capacity * self.W)
+            h.alloc("ew_val", 4 * self.ew_capacity * self.W)
+            h.alloc("ew_cnt", 256 * self.W)
+        self.nbuckets = nb
+
+        self.flat_params = h.tensor("params")
+        self.flat_grads = h.tensor("grads")
+        self.signals = h.tensor("signals", torch.int32)
+        bind_parameters(self.model, self.flat_params, self.layout)
+        self.grad_views = bind_gradients(self.model, self.flat_grads, self.layout)
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)  # activations only; weights stay flat views
+            bind_parameters(self.model, self.flat_params, self.layout)
+
+        # ---- device tables --------------------------------------------------------------------
+        dev = self.device
+        self.t_layers = _dev_bytes(self.plan.layers_bytes(), dev)
+        self.t_enc_tiles = _dev_bytes(P.Plan.tiles_bytes(self.plan.enc_tiles), dev)
+        self.t_ps_tiles = _dev_bytes(P.Plan.tiles_bytes(self.plan.ps_tiles), dev)
+        self.t_dense_tiles = _dev_bytes(P.Plan.tiles_bytes(self.plan.dense_tiles), dev)
+        self.t_ts_layers = torch.tensor(self.plan.ts_layers or [0], dtype=torch.int32, device=dev)
+        n_ts = max(len(self.plan.ts_layers), 1)
+        self.gpart = torch.zeros(self.plan.gpart_floats, dtype=torch.float32, device=dev)
+        self.vsel = torch.zeros(n_ts * P.TS_MAX_COLS * P.RCAP_MAX, dtype=torch.float32, device=dev)
+        self.selcount = torch.zeros(n_ts, dtype=torch.int32, device=dev)
+        self.sigma = torch.zeros(n_ts * P.TS_MAX_COLS, dtype=torch.float32, device=dev)
+        self.ctrl = _dev_bytes(P.pack_ctrl(step=1, lr=lr, momentum=momentum, dampening=dampening,
+                                           weight_decay=weight_decay, nesterov=nesterov, first_step=1, seed=seed), dev)
+        self.ctrl_i32 = self.ctrl.view(torch.int32)
+        self.ctrl_f32 = self.ctrl.view(torch.float32)
+        ranks = list(range(world))
+        workers = list(range(self.first_worker, world))
+        self.t_params_peer = torch.tensor([h.region_ptr("params", r) for r in ranks], dtype=torch.int64, device=dev)
+        self.t_grads_peer = torch.tensor([h.region_ptr("grads", r) for r in workers], dtype=torch.int64, device=dev)
+        self.t_flag_peer = torch.tensor([h.region_ptr("signals", r) + 4 * PARAM_FLAG_SLOT for r in ranks],
+                                        dtype=torch.int64, device=dev)
+        self.params_mc = h.region_mc_ptr("params")
+        self.grads_mc = h.region_mc_ptr("grads")
+        self.ps_push_flags = h.region_ptr("signals", 0)           # on the PS
+        self.local_param_flag = h.region_ptr("signals") + 4 * PARAM_FLAG_SLOT
+        if self.is_ps:
+            self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        if self.code in ("qsgd", "terngrad", "entrywise"):
+            self.dense_plan = P.dense_only_plan(shapes, offsets=self.layout.offsets)
+            self.t_dense_layers = _dev_bytes(self.dense_plan.layers_bytes(), dev)
+            self.t_dense_ps_tiles = _dev_bytes(P.Plan.tiles_bytes(self.dense_plan.ps_tiles), dev)
+            if self.is_ps:
+                self.out_sum = torch.zeros(total, dtype=torch.float32, device=dev)
+                self.t_out_sum_ptr = torch.tensor([self.out_sum.data_ptr()], dtype=torch.int64, device=dev)
+        if self.code in ("qsgd", "terngrad") and self.is_ps:
+            wb, nbs = h.region_ptr("qwords", 0), h.region_ptr("qnorms", 0)
+            self.t_qwords = torch.tensor([wb + 8 * nb * self.q_words * w for w in range(self.W)], dtype=torch.int64, device=dev)
+            self.t_qnorms = torch.tensor([nbs + 4 * nb * w for w in range(self.W)], dtype=torch.int64, device=dev)
+        if self.code == "terngrad":
+            self.clip = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self.code == "entrywise":
+            self.l1 = torch.zeros(len(shapes), dtype=torch.float32, device=dev)
+            self.ew_local_count = torch.zeros(1, dtype=torch.int32, device=dev)
+            if self.is_ps:
+                ib, vb, cb = (h.region_ptr(n, 0) for n in ("ew_idx", "ew_val", "ew_cnt"))
+                self.t_ew_idx = torch.tensor([ib + 4 * self.ew_capacity * w for w in range(self.W)], dtype=torch.int64, device=dev)
+                self.t_ew_val = torch.tensor([vb + 4 * self.ew_capacity * w for w in range(self.W)], dtype=torch.int64, device=dev)
+                self.t_ew_cnt = torch.tensor([cb + 256 * w for w in range(self.W)], dtype=torch.int64, device=dev)
+        sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.ps_grid = min(len(self.plan.ps_tiles), sm * 3)
+
+        # ---- metrics + static batch ----------------------------------------------------------
+        self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)  # loss, prec1, prec5
+        self.static_x = None
+        self.static_y = None
+        self.graph = None
+
+        self._initial_sync()
+
+    # ------------------------------------------------------------------------------------------
+    def _entry_expected(self, total: int) -> float:
+        b = self.entry_budget
+        return b * total if b < 1.0 else b * len(self.layout.shapes)
+
+    def _barrier(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _initial_sync(self):
+        """K8: every rank starts from rank 0's parameters; flags say 'step 1 ready'."""
+        self._barrier()
+        if self.is_ps and self.world > 1:
+            self.C.param_bcast(self.flat_params, self.t_params_peer, self.params_mc, self.world, self.rank,
+                               self.plan.total_elems)
+        self._barrier()
+        self.signals.zero_()
+        self.signals[PARAM_FLAG_SLOT] = 1
+        self._barrier()
+
+    def set_lr(self, lr: float):
+        self.lr = lr
+        self.ctrl_f32[2] = lr  # Ctrl::lr (device write ordered on the stream)
+
+    def error_code(self) -> int:
+        return int(self.ctrl_i32[1].item())
+
+    def device_step(self) -> int:
+        return int(self.ctrl_i32[0].item())
+
+    # ------------------------------------------------------------------------------------------
+    def _forward_backward(self):
+        x, y = self.static_x, self.static_y
+        if self.autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = self.model(x)
+                loss = self.criterion(logits.float(), y)
+        else:
+            logits = self.model(x)
+            loss = self.criterion(logits, y)
+        loss.backward()
+        with torch.no_grad():
+            lg = logits.detach().float()
+            k = min(5, lg.size(1))
+            top = lg.topk(k, 1).indices
+            hit = top.eq(y.view(-1, 1))
+            self.loss_buf[0] = loss.detach()
+            self.loss_buf[1] = hit[:, :1].float().sum() * (100.0 / y.numel())
+            self.loss_buf[2] = hit.float().sum() * (100.0 / y.numel())
+
+    def _encode_push(self):
+        C, pl = self.C, self.plan
+        n = 0
+        if self.code == "svd":
+            arena0 = self.heap.region_ptr("arena", 0)
+            if pl.enc_tiles:
+                C.gram(self.flat_grads, self.t_layers, self.t_enc_tiles, len(pl.enc_tiles), self.gpart)
+                C.eig_sample(self.t_layers, self.t_ts_layers, self.gpart, self.vsel, self.selcount, self.sigma,
+                             arena0, pl.arena_floats, self.ctrl, None, self.svd_rank, self.random_sample,
+                             self.waterfill, self.systematic, self.worker_index)
+                n += 2
+            C.project_push(self.flat_grads, self.t_layers, self.t_enc_tiles, len(pl.enc_tiles), self.vsel,
+                           self.selcount, arena0, pl.arena_floats, self.ps_push_flags, self.ctrl,
+                           self.worker_index, True)
+            n += 1
+        elif self.code == "sgd":
+            C.signal_push(self.ps_push_flags, self.ctrl, self.worker_index)
+            n += 1
+        elif self.code in ("qsgd", "terngrad"):
+            total, nb = pl.total_elems, self.nbuckets
+            tern = self.code == "terngrad"
+            clip = None
+            if tern:
+                self.clip.copy_((2.5 * self.flat_grads.std(unbiased=False)).reshape(1))
+                clip = self.clip
+            wout = self.heap.region_ptr("qwords", 0) + 8 * nb * self.q_words * self.worker_index
+            nout = self.heap.region_ptr("qnorms", 0) + 4 * nb * self.worker_index
+            C.qsgd_encode(self.flat_grads, total, self.bucket, self.q, tern, clip, wout, nout, self.ctrl,
+                          self.worker_index, None)
+            C.signal_push(self.ps_push_flags, self.ctrl, self.worker_index)
+            n += 2
+        elif self.code == "entrywise":
+            w = self.worker_index
+            C.entrywise_encode(self.flat_grads, self.t_layers, self.t_dense_tiles, len(pl.dense_tiles), self.l1,
+                               self.entry_budget, self.heap.region_ptr("ew_idx", 0) + 4 * self.ew_capacity * w,
+                               self.heap.region_ptr("ew_val", 0) + 4 * self.ew_capacity * w,
+                               self.heap.region_ptr("ew_cnt", 0) + 256 * w, self.ew_capacity, self.ew_local_count,
+                               self.ps_push_flags, self.ctrl, w, None, True)
+            n += 2
+        else:
+            raise ValueError("unsupported --code for the fused engine: %s" % self.code)
+        return n
+
+    def _ps_update(self):
+        C, pl = self.C, self.plan
+        n = 0
+        if self.code in ("svd", "sgd"):
+            arenas = self.heap.region_ptr("arena", 0) if self.code == "svd" else 0
+            C.ps_update(self.t_layers, self.t_ps_tiles, len(pl.ps_tiles), self.W, self.W, self.world,
+                        self.flat_params, self.momentum_buf, self.t_params_peer, self.params_mc, self.t_grads_peer,
+                        self.grads_mc, arenas, pl.arena_floats, self.ps_push_flags, self.t_flag_peer, self.ctrl,
+                        self.timeout_ticks, 1.0 / self.W, self.ps_grid)
+            return 1
+        if self.code in ("qsgd", "terngrad"):
+            C.qsgd_decode_sum(self.t_qwords, self.t_qnorms, self.W, pl.total_elems, self.bucket, self.q,
+                              self.code == "terngrad", self.out_sum, self.ps_push_flags, self.ctrl,
+                              self.timeout_ticks)
+            n += 1
+        elif self.code == "entrywise":
+            C.entrywise_scatter(self.t_ew_idx, self.t_ew_val, self.t_ew_cnt, self.W, self.ew_capacity, self.out_sum,
+                                pl.total_elems, self.ps_push_flags, self.ctrl, self.timeout_ticks)
+            n += 1
+        dp = self.dense_plan
+        C.ps_update(self.t_dense_layers, self.t_dense_ps_tiles, len(dp.ps_tiles), 1, 0, self.world,
+                    self.flat_params, self.momentum_buf, self.t_params_peer, self.params_mc, self.t_out_sum_ptr, 0,
+                    0, dp.arena_floats, self.ps_push_flags, self.t_flag_peer, self.ctrl, self.timeout_ticks,
+                    1.0 / self.W, min(len(dp.ps_tiles), self.ps_grid))
+        return n + 1
+
+    def _step_body(self):
+        """One full step on the current stream (capturable)."""
+        C = self.C
+        n = 0
+        C.wait_params(self.local_param_flag, self.ctrl, self.timeout_ticks); n += 1
+        if self.is_worker:
+            self.flat_grads.zero_()
+            self._forward_backward()
+            n += self._encode_push()
+        if self.is_ps:
+            n += self._ps_update()
+        C.advance_step(self.ctrl); n += 1
+        self.launches_per_step = n
+
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, x_example: torch.Tensor, y_example: torch.Tensor, warmup: int = 3):
+        """Allocate static inputs, warm up eagerly, then capture the step in a CUDA graph."""
+        self.static_x = torch.empty_like(x_example, device=self.device)
+        if self.channels_last and self.static_x.dim() == 4:
+            self.static_x = self.static_x.contiguous(memory_format=torch.channels_last)
+        self.static_y = torch.empty_like(y_example, device=self.device)
+        self.static_x.copy_(x_example)
+        self.static_y.copy_(y_example)
+        self.model.train()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_body()
+                self.step += 1
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            # capture does not execute: the device step counter is unchanged
+        return self
+
+    def train_step(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None):
+        """Run one step.  ``x``/``y`` may live in pinned host memory (async H2D)."""
+        if x is not None and self.is_worker:
+            self.static_x.copy_(x, non_blocking=True)
+            self.static_y.copy_(y, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+        self.step += 1
+        return self.loss_buf
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.graph = None
+        self.heap.close()
+
+
+# ----------------------------------------------------------------------------------------------
+def run_p2p_training(args):
+    """``--backend p2p`` entry of the launcher: every GPU trains, GPU 0 also hosts the PS."""
+    import time
+
+    from ..data import DataLoader, build_datasets, shard_dataset
+    from ..models import build_model
+    from ..utils import checkpoint as ckpt
+    from ..utils.logging import master_line, test_line, worker_line
+    from .nn_ops import accuracy
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", args.master_addr)
+        os.environ.setdefault("MASTER_PORT", str(args.master_port))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.manual_seed(args.seed)  # identical init on every rank; rank 0's copy is broadcast anyway
+    train_set, test_set, num_classes = build_datasets(
+        args.dataset, args.data_root, synthetic=args.synthetic, seed=args.seed,
+        train_len=args.train_len or None, test_len=args.test_len or None)
+    model = build_model(args.network, num_classes, args.dataset)
+    eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr,
+                      momentum=args.momentum, weight_decay=args.weight_decay, nesterov=args.nesterov,
+                      ps_mode=args.ps_mode, sampling=args.sampling, prob_rule=args.prob_rule, seed=args.seed,
+                      quantization_level=args.quantization_level, bucket_size=args.bucket_size,
+                      entry_budget=args.entry_budget, dtype=args.dtype)
+    first = 0 if args.ps_mode == "colocated" or world == 1 else 1
+    nworkers = world - first
+    shard = shard_dataset(train_set, max(rank - first, 0), nworkers, seed=args.seed)
+    loader = DataLoader(shard, batch_size=args.batch_size, shuffle=True, seed=args.seed + rank, drop_last=True,
+                        pin_memory=True, prefetch=2)
+    test_loader = torch.utils.data.DataLoader(test_set, batch_size=args.test_batch_size, shuffle=False)
+    x0, y0 = loader.next_batch()
+    eng.prepare(x0, y0, warmup=0 if args.max_steps < 8 else 3)
+    n_data, base_lr, shrink = len(shard), args.lr, 0
+    msg_mb = (eng.plan.factor_bytes_per_worker() + eng.plan.dense_bytes()) / 2 ** 20
+    while eng.step <= args.max_steps:
+        t0 = time.time()
+        x, y = loader.next_batch()
+        stats = eng.train_step(x, y)
+        cur = eng.step - 1
+        if cur % args.log_interval == 0 or cur == args.max_steps:
+            loss, p1, p5 = stats.tolist()
+            dt = time.time() - t0
+            if eng.is_worker:
+                print(worker_line(rank, cur, loader.epochs_completed, (cur * args.batch_size) % n_data, n_data, loss,
+                                  dt, dt, 0.0, 0.0, msg_mb, p1, p5))
+            if eng.is_ps:
+                print(master_line(cur, 0.0, eng.lr, 0.0))
+        if cur % args.eval_freq == 0:
+            if eng.is_ps:
+                ckpt.save_model(args.train_dir, cur, eng.model)
+            if eng.is_worker and rank == first:
+                eng.model.eval()
+                tl, a1, a5, nbt, cnt = 0.0, 0.0, 0.0, 0, 0
+                with torch.no_grad():
+                    for i, (dx, dy) in enumerate(test_loader):
+                        if args.eval_batches and i >= args.eval_batches:
+                            break
+                        dx, dy = dx.to(dev), dy.to(dev)
+                        out = eng.model(dx)
+                        tl += F.cross_entropy(out, dy, reduction="sum").item()
+                        b1, b5 = accuracy(out, dy, (1, 5))
+                        a1 += b1.item(); a5 += b5.item(); nbt += 1; cnt += len(dy)
+                print(test_line(cur, tl / max(cnt, 1), a1 / max(nbt, 1), a5 / max(nbt, 1)))
+                eng.model.train()
+        if eng.step % 50 == 0:  # shrinkage_freq (master:232-234), actually applied here
+            shrink += 1
+            eng.set_lr(base_lr * args.lr_shrinkage ** shrink)
+    err = eng.error_code()
+    if err:
+        print("rank %d: device error code %d" % (rank, err))
+    loader.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()

@@ -1,0 +1,145 @@
+"""Coder oracles: unbiasedness, variance sanity, round trips, reference parity."""
+import math
+
+import pytest
+import torch
+
+from atomo_b200 import codings
+from atomo_b200.codings.sampling import atom_probabilities, sample_atoms
+from atomo_b200.codings.svd import matricize_shape, resize_to_2d
+
+
+def test_registry_lists_all_coders():
+    for name in ("sgd", "svd", "qsgd", "terngrad", "entrywise", "qsvd", "dense", "lossless"):
+        assert name in codings.available()
+    with pytest.raises(ValueError):
+        codings.build("nope")
+
+
+@pytest.mark.parametrize("shape,expect", [
+    ((10,), (5, 2)), ((7,), (7, 1)), ((8, 4), (8, 4)), ((6, 4, 1, 1), (6, 4)),
+    ((64, 32, 3, 3), (1024, 18)), ((20, 1, 5, 5), (10, 50)), ((3, 5, 3, 3), (15, 9)),
+])
+def test_matricize_rules(shape, expect):
+    # svd.py:12-28
+    assert matricize_shape(shape) == expect
+    assert tuple(resize_to_2d(torch.zeros(shape)).shape) == expect
+
+
+def test_probability_rules():
+    s = torch.tensor([10.0, 5.0, 1.0, 0.5, 0.0])
+    p_ref = atom_probabilities(s, 3, "reference")
+    assert torch.allclose(p_ref, torch.tensor([1.0, 15 / 16.5, 3 / 16.5, 1.5 / 16.5, 0.0]), atol=1e-6)
+    p_wf = atom_probabilities(s, 3, "waterfill")
+    assert abs(float(p_wf.sum()) - 3.0) < 1e-5 and float(p_wf.max()) <= 1.0
+    p0 = atom_probabilities(s, 0)
+    assert torch.allclose(p0, s / 10.0)
+
+
+def test_systematic_sampling_fixed_count_and_marginals():
+    g = torch.Generator().manual_seed(0)
+    p = atom_probabilities(torch.tensor([9.0, 4.0, 3.0, 2.0, 1.0, 1.0]), 3, "waterfill")
+    counts = torch.zeros(6)
+    for _ in range(4000):
+        idx = sample_atoms(p, "systematic", generator=g)
+        assert len(idx) == 3
+        counts[idx] += 1
+    assert torch.allclose(counts / 4000, p.float(), atol=0.03)
+
+
+@pytest.mark.parametrize("scheme,rule", [("bernoulli", "reference"), ("systematic", "waterfill")])
+def test_svd_unbiased(scheme, rule):
+    torch.manual_seed(0)
+    g = torch.randn(24, 6, 3, 3) * torch.linspace(1, 0.1, 6).view(1, 6, 1, 1)
+    coder = codings.build("svd", rank=3, prob_rule=rule, scheme=scheme, generator=torch.Generator().manual_seed(1))
+    acc = torch.zeros_like(g)
+    n = 600
+    for _ in range(n):
+        acc += coder.decode(coder.encode(g))
+    rel = float((acc / n - g).norm() / g.norm())
+    assert rel < 0.12, rel
+
+
+def test_svd_code_layout_and_topk():
+    g = torch.randn(16, 8, 3, 3)
+    code = codings.build("svd", rank=2, random_sample=False).encode(g)
+    assert set(code) >= {"u", "s", "vT", "orig_size", "reshaped", "encode", "rank"}
+    assert code["u"].shape == (64, 2) and code["vT"].shape == (2, 18) and code["reshaped"]
+    full = codings.build("svd", rank=18, random_sample=False)
+    assert torch.allclose(full.decode(full.encode(g)), g, atol=1e-4)
+    passthrough = codings.build("svd", compress=False)
+    assert torch.equal(passthrough.decode(passthrough.encode(g)), g)
+
+
+@pytest.mark.parametrize("scheme", ["qsgd", "terngrad"])
+def test_qsgd_unbiased_and_packing(scheme):
+    torch.manual_seed(0)
+    g = torch.randn(3, 700)
+    coder = codings.build(scheme, quantization_level=4, bucket_size=512, generator=torch.Generator().manual_seed(2))
+    code = coder.encode(g)
+    E, L = 64 // 6, (512 + 9) // 10
+    assert code["words"].shape == (5, L) and code["words"].dtype == torch.int64 and E == 10
+    acc = torch.zeros_like(g)
+    n = 300
+    for _ in range(n):
+        acc += coder.decode(coder.encode(g))
+    err = (acc / n - g)
+    if scheme == "qsgd":
+        assert float(err.abs().mean()) < 0.08
+    else:  # terngrad clips at 2.5 sigma: unbiased only inside the clip range
+        inside = g.abs() < 2.4 * g.std()
+        assert float(err[inside].abs().mean()) < 0.05
+
+
+def test_qsgd_levels_never_overflow():
+    g = torch.zeros(512)
+    g[3] = 5.0  # one element carries the whole norm (qsgd.py edge case in SURVEY 2.8)
+    coder = codings.build("qsgd", quantization_level=2, bucket_size=512)
+    out = coder.decode(coder.encode(g))
+    assert torch.allclose(out, g)
+
+
+def test_entrywise_unbiased_and_budget():
+    torch.manual_seed(0)
+    g = torch.randn(40, 50)
+    coder = codings.build("entrywise", budget=0.1, generator=torch.Generator().manual_seed(3))
+    cnt, acc, n = 0, torch.zeros_like(g), 400
+    for _ in range(n):
+        code = coder.encode(g)
+        cnt += code["idx"].numel()
+        acc += coder.decode(code)
+    assert cnt / n <= 0.1 * g.numel() * 1.05
+    assert float((acc / n - g).norm() / g.norm()) < 0.2
+    sys_coder = codings.build("entrywise", budget=0.1, prob_rule="waterfill", scheme="systematic")
+    assert abs(sys_coder.encode(g)["idx"].numel() - 200) <= 1
+
+
+def test_qsvd_roundtrip_shape_and_unbiased():
+    torch.manual_seed(0)
+    g = torch.randn(16, 4, 3, 3)
+    coder = codings.build("qsvd", rank=3, quantization_level=6)
+    acc, n = torch.zeros_like(g), 300
+    for _ in range(n):
+        acc += coder.decode(coder.encode(g))
+    assert float((acc / n - g).norm() / g.norm()) < 0.25
+
+
+def test_lossless_and_wire_bytes():
+    g = torch.randn(33, 7)
+    for kw in ({}, {"compress": True}):
+        c = codings.build("sgd", **kw)
+        code = c.encode(g)
+        assert torch.equal(c.decode(code), g)
+        assert codings.Coding.wire_bytes(code) > 0
+    from atomo_b200.utils.compress import compress, decompress
+    assert decompress(compress(b"abc" * 100, level=5)) == b"abc" * 100
+    with pytest.raises(ValueError):
+        compress(b"x", name="lz4")
+
+
+def test_indicators():
+    from atomo_b200.codings.utils import l1_indicator, nuclear_indicator
+    a = torch.outer(torch.randn(30), torch.randn(8))  # rank-1: spectral atoms win
+    s = torch.linalg.svdvals(a)
+    assert nuclear_indicator(a, s) == pytest.approx(float(s.sum()) * math.sqrt(38))
+    assert l1_indicator(a) == pytest.approx(float(a.abs().sum()), rel=1e-5)
