@@ -30,7 +30,7 @@ void atomo_launch_gram(const float* grad, const void* layers, const void* tiles,
 void atomo_launch_eig_sample(const void* layers, const int* ts_layers, int n_ts, const float* gpart, float* vsel,
                              int* selcount, float* sigma_out, float* ps_arena_peer, long long arena_floats,
                              const void* ctrl, const float* ext_uniforms, int rank, int random_sample,
-                             int waterfill, int systematic, int worker_index, cudaStream_t stream);
+                             int waterfill, int systematic, int worker_index, int threads, cudaStream_t stream);
 void atomo_launch_project_push(const float* grad, const void* layers, const void* tiles, int ntiles,
                                const float* vsel, const int* selcount, float* ps_arena_peer,
                                long long arena_floats, int* push_flag_peer, void* ctrl, int worker_index,
@@ -122,14 +122,14 @@ void eig_sample(const torch::Tensor& layers, const torch::Tensor& ts_layers, con
                 torch::Tensor vsel, torch::Tensor selcount, c10::optional<torch::Tensor> sigma_out,
                 uint64_t ps_arena_peer, int64_t arena_floats, const torch::Tensor& ctrl,
                 c10::optional<torch::Tensor> ext_uniforms, int rank, bool random_sample, bool waterfill,
-                bool systematic, int worker_index) {
+                bool systematic, int worker_index, int threads) {
   c10::cuda::CUDAGuard guard(gpart.device());
   atomo_launch_eig_sample(layers.data_ptr(), ts_layers.data_ptr<int>(), (int)ts_layers.numel(),
                           gpart.data_ptr<float>(), vsel.data_ptr<float>(), selcount.data_ptr<int>(),
                           sigma_out.has_value() ? sigma_out->data_ptr<float>() : nullptr, P<float>(ps_arena_peer),
                           arena_floats, ctrl.data_ptr(),
                           ext_uniforms.has_value() ? ext_uniforms->data_ptr<float>() : nullptr, rank,
-                          random_sample, waterfill, systematic, worker_index, cur_stream());
+                          random_sample, waterfill, systematic, worker_index, threads, cur_stream());
 }
 
 void project_push(const torch::Tensor& grad, const torch::Tensor& layers, const torch::Tensor& tiles, int ntiles,
@@ -254,7 +254,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &tensor_from_ptr);
   // kernels
   m.def("gram", &gram);
-  m.def("eig_sample", &eig_sample);
+  m.def("eig_sample", &eig_sample, py::arg("layers"), py::arg("ts_layers"), py::arg("gpart"), py::arg("vsel"),
+        py::arg("selcount"), py::arg("sigma_out"), py::arg("ps_arena_peer"), py::arg("arena_floats"), py::arg("ctrl"),
+        py::arg("ext_uniforms"), py::arg("rank"), py::arg("random_sample"), py::arg("waterfill"),
+        py::arg("systematic"), py::arg("worker_index"), py::arg("threads") = 256);
   m.def("project_push", &project_push);
   m.def("signal_push", &signal_push);
   m.def("ps_update", &ps_update);

@@ -27,7 +27,7 @@ constexpr int GRAM_THREADS = 256;
 constexpr int GRAM_CHUNK = 64;   // rows staged per iteration
 constexpr int EIG_THREADS = 256;
 constexpr int PROJ_THREADS = 128;
-constexpr int MAX_SWEEPS = 10;
+constexpr int MAX_SWEEPS = 12;
 
 // ----------------------------------------------------------------------------
 // stage a chunk of tall rows into shared memory: sm[r*stride + c] = A[row0+r][c]
@@ -139,7 +139,7 @@ __device__ __forceinline__ void rr_pair(int ne, int rnd, int k, int& p, int& q) 
   p = min(a, b); q = max(a, b);
 }
 
-__global__ void __launch_bounds__(EIG_THREADS)
+__global__ void __launch_bounds__(1024)
 eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ ts_layers,
                   const float* __restrict__ gpart, float* __restrict__ vsel, int* __restrict__ selcount,
                   float* __restrict__ sigma_out, float* ps_arena_peer, long long arena_floats, const Ctrl* ctrl,
@@ -152,7 +152,8 @@ eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ 
   __shared__ int order[TS_MAX_COLS];  // order[k] = index of k-th largest sigma
   __shared__ int sel[RCAP_MAX];
   __shared__ float selscale[RCAP_MAX];
-  __shared__ float s_off2, s_diag2;
+  __shared__ int s_maxrel;
+  __shared__ float s_gmax;
   __shared__ int s_count, s_done;
 
   const int layer_id = ts_layers[blockIdx.x];
@@ -161,12 +162,16 @@ eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ 
   const int tid = threadIdx.x;
   const int step = ctrl->step;
 
-  // ---- G = sum of tile partials; V = I --------------------------------------
-  for (int e = tid; e < n * n; e += blockDim.x) {
-    const float* gp = gpart + L.gpart_off + e;
+  // ---- G = sum of tile partials (padded to an even size with a zero row/col); V = I ----------
+  const int ne = n + (n & 1);
+  const int npairs = ne >> 1;
+  for (int e = tid; e < ne * ne; e += blockDim.x) {
+    const int i = e / ne, j = e - i * ne;
     float s = 0.f;
-    for (int t = 0; t < L.ntiles; ++t) s += gp[(long long)t * n * n];
-    int i = e / n, j = e - i * n;
+    if (i < n && j < n) {
+      const float* gp = gpart + L.gpart_off + i * n + j;
+      for (int t = 0; t < L.ntiles; ++t) s += gp[(long long)t * n * n];
+    }
     G[i * GS + j] = s;
     V[i * GS + j] = (i == j) ? 1.f : 0.f;
   }
@@ -182,72 +187,69 @@ eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ 
   }
   __syncthreads();
 
-  // ---- cyclic Jacobi with round-robin (parallel) ordering -------------------
-  const int ne = n + (n & 1);
-  const int npairs = ne >> 1;
-  if (n > 1) {
+  // ---- cyclic Jacobi, round-robin (parallel) ordering, fused two-sided update ------------------
+  // All ne/2 pairs of a round are disjoint, so G' = J^T G J decomposes into independent 2x2
+  // blocks: block (k1,k2) = J_k1^T * G[{p1,q1}][{p2,q2}] * J_k2 — one thread per block, one
+  // barrier between "compute rotations" and "apply", none between the row and column halves.
+  // The padded dummy index only ever meets zeros, so its rotations are the identity.
+  if (tid == 0) {
+    float g = 0.f;
+    for (int i = 0; i < n; ++i) g = fmaxf(g, fabsf(G[i * GS + i]));
+    s_gmax = g;
+  }
+  __syncthreads();
+  const float gmax = s_gmax;
+  if (n > 1 && gmax > 0.f) {
     for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
-      if (tid == 0) { s_off2 = 0.f; s_diag2 = 0.f; }
+      if (tid == 0) s_maxrel = 0;
       __syncthreads();
-      {
-        float off2 = 0.f, diag2 = 0.f;
-        for (int e = tid; e < n * n; e += blockDim.x) {
-          int i = e / n, j = e - i * n;
-          float v = G[i * GS + j];
-          if (i == j) diag2 += v * v; else off2 += v * v;
-        }
-        off2 = warp_sum(off2); diag2 = warp_sum(diag2);
-        if ((tid & 31) == 0) { atomicAdd(&s_off2, off2); atomicAdd(&s_diag2, diag2); }
-      }
-      __syncthreads();
-      if (s_off2 <= 1e-12f * s_diag2) break;  // uniform across the CTA (shared values)
       for (int rnd = 0; rnd < ne - 1; ++rnd) {
         if (tid < npairs) {
           int p, q;
           rr_pair(ne, rnd, tid, p, q);
           float c = 1.f, s = 0.f;
-          if (q < n) {
-            const float apq = G[p * GS + q], app = G[p * GS + p], aqq = G[q * GS + q];
-            if (fabsf(apq) > 1e-12f * sqrtf(fabsf(app * aqq)) && apq != 0.f) {
-              const float tau = (aqq - app) / (2.f * apq);
-              const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-              c = rsqrtf(1.f + t * t);
-              s = t * c;
-            }
-          } else {
-            q = -1;  // bye (odd n)
+          const float apq = G[p * GS + q], app = G[p * GS + p], aqq = G[q * GS + q];
+          const float scale = sqrtf(fabsf(app * aqq));
+          // rotate unless the coupling is below fp32 noise (relative to the pair and to the spectrum)
+          if (fabsf(apq) > 1e-7f * scale && fabsf(apq) > 3e-7f * gmax) {
+            const float tau = (aqq - app) / (2.f * apq);
+            const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+            c = rsqrtf(1.f + t * t);
+            s = t * c;
+            atomicMax(&s_maxrel, __float_as_int(fabsf(apq) / gmax));
           }
           rp[tid] = p; rq[tid] = q; rc[tid] = c; rs[tid] = s;
         }
         __syncthreads();
-        // column update of G and V:  X <- X J
-        for (int e = tid; e < npairs * n; e += blockDim.x) {
-          const int k = e / n, i = e - k * n;
-          const int q = rq[k];
-          if (q < 0) continue;
-          const int p = rp[k];
-          const float c = rc[k], s = rs[k];
-          const float gp_ = G[i * GS + p], gq_ = G[i * GS + q];
-          G[i * GS + p] = c * gp_ - s * gq_;
-          G[i * GS + q] = s * gp_ + c * gq_;
-          const float vp = V[i * GS + p], vq = V[i * GS + q];
-          V[i * GS + p] = c * vp - s * vq;
-          V[i * GS + q] = s * vp + c * vq;
-        }
-        __syncthreads();
-        // row update of G:  G <- J^T G
-        for (int e = tid; e < npairs * n; e += blockDim.x) {
-          const int k = e / n, j = e - k * n;
-          const int q = rq[k];
-          if (q < 0) continue;
-          const int p = rp[k];
-          const float c = rc[k], s = rs[k];
-          const float gp_ = G[p * GS + j], gq_ = G[q * GS + j];
-          G[p * GS + j] = c * gp_ - s * gq_;
-          G[q * GS + j] = s * gp_ + c * gq_;
+        const int nblk = npairs * npairs;
+        for (int e = tid; e < nblk + npairs * ne; e += blockDim.x) {
+          if (e < nblk) {
+            const int k1 = e / npairs, k2 = e - k1 * npairs;
+            const int p1 = rp[k1], q1 = rq[k1], p2 = rp[k2], q2 = rq[k2];
+            const float c1 = rc[k1], s1 = rs[k1], c2 = rc[k2], s2 = rs[k2];
+            const float a = G[p1 * GS + p2], b = G[p1 * GS + q2], c_ = G[q1 * GS + p2], d = G[q1 * GS + q2];
+            // left: rows (p1,q1) <- J1^T
+            const float ra = c1 * a - s1 * c_, rb = c1 * b - s1 * d;
+            const float rc_ = s1 * a + c1 * c_, rd = s1 * b + c1 * d;
+            // right: cols (p2,q2) <- J2
+            G[p1 * GS + p2] = c2 * ra - s2 * rb;
+            G[p1 * GS + q2] = s2 * ra + c2 * rb;
+            G[q1 * GS + p2] = c2 * rc_ - s2 * rd;
+            G[q1 * GS + q2] = s2 * rc_ + c2 * rd;
+          } else {
+            const int f = e - nblk;
+            const int k = f / ne, i = f - k * ne;
+            const int p = rp[k], q = rq[k];
+            const float c = rc[k], s = rs[k];
+            const float vp = V[i * GS + p], vq = V[i * GS + q];
+            V[i * GS + p] = c * vp - s * vq;
+            V[i * GS + q] = s * vp + c * vq;
+          }
         }
         __syncthreads();
       }
+      // quadratic convergence: couplings below 1e-3 at the start of a sweep are ~1e-6 after it
+      if (__int_as_float(s_maxrel) < 1e-3f) break;  // shared value, uniform across the CTA
     }
   }
   __syncthreads();
@@ -490,10 +492,12 @@ void atomo_launch_gram(const float* grad, const void* layers, const void* tiles,
 void atomo_launch_eig_sample(const void* layers, const int* ts_layers, int n_ts, const float* gpart, float* vsel,
                              int* selcount, float* sigma_out, float* ps_arena_peer, long long arena_floats,
                              const void* ctrl, const float* ext_uniforms, int rank, int random_sample,
-                             int waterfill, int systematic, int worker_index, cudaStream_t stream) {
+                             int waterfill, int systematic, int worker_index, int threads, cudaStream_t stream) {
   if (n_ts <= 0) return;
+  if (threads < 64) threads = EIG_THREADS;
+  if (threads > 1024) threads = 1024;
   EncodeCfg cfg{rank, random_sample, waterfill, systematic, worker_index, ext_uniforms != nullptr};
-  eig_sample_kernel<<<n_ts, EIG_THREADS, 0, stream>>>((const LayerDesc*)layers, ts_layers, gpart, vsel, selcount,
+  eig_sample_kernel<<<n_ts, threads, 0, stream>>>((const LayerDesc*)layers, ts_layers, gpart, vsel, selcount,
                                                         sigma_out, ps_arena_peer, arena_floats, (const Ctrl*)ctrl,
                                                         ext_uniforms, cfg);
 }

@@ -152,7 +152,10 @@ def build_plan(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 3
         route = ROUTE_DENSE
         if code == "svd":
             is_vector = len(shape) <= 1
-            if not (is_vector and dense_vectors) and 2 <= cols <= TS_MAX_COLS and rows >= cols:
+            # tall-skinny Gram/Jacobi path: cols <= 32 always; 32 < cols <= 64 only when really
+            # tall (the Jacobi cost grows ~cols^3 and sits on the critical path)
+            skinny = cols <= 32 or (cols <= TS_MAX_COLS and rows >= 8 * cols)
+            if not (is_vector and dense_vectors) and cols >= 2 and rows >= cols and skinny:
                 route = ROUTE_SVD_TS
         layers.append(Layer(i, shape, this_off, numel, rows, cols, rs, cs, route))
         off = this_off + _round_up(numel, ALIGN_ELEMS)

@@ -49,6 +49,7 @@ class Transport:
     def push(self, codes: list, step: int) -> int: raise NotImplementedError
     def gather(self, step: int, need: Optional[int] = None): raise NotImplementedError
     def send_kill(self, worker_rank: int) -> None: raise NotImplementedError
+    def drain(self) -> int: return 0
     def kill_requested(self) -> bool: return False
     def barrier(self) -> None: raise NotImplementedError
 
@@ -68,10 +69,14 @@ class TorchDistTransport(Transport):
         self.device = device
         self.timeout_s = timeout_s
         self._stale_dropped = 0
+        self._rounds = 0                      # steps broadcast so far (PS side)
+        self._recv_count: Dict[int, int] = {}  # messages received per worker (PS side)
         self.bytes_sent = 0
 
     # -- step handshake -------------------------------------------------
     def send_step(self, step: int) -> None:
+        if step != STOP_STEP:
+            self._rounds += 1
         t = torch.tensor([step], dtype=torch.int64, device=self.device)
         reqs = [dist.isend(t, dst=w, group=self.group, tag=10) for w in range(1, self.world_size)]
         for r in reqs:
@@ -131,12 +136,24 @@ class TorchDistTransport(Transport):
             else:
                 sender, msg_step, buf = self._recv_one(order[cursor])
                 cursor += 1
+            self._recv_count[sender] = self._recv_count.get(sender, 0) + 1
             if msg_step == step:
                 got[sender] = wire.unpack(buf)["codes"]
             else:  # stale gradient from a straggler: drop
                 self._stale_dropped += 1
-        # workers that did not make the cut still owe us a (stale) message
         return got
+
+    def drain(self) -> int:
+        """PS side, before STOP: receive (and drop) the messages stragglers still owe
+        us, so no worker is left blocked in a send when the PS exits."""
+        dropped = 0
+        for w in range(1, self.world_size):
+            while self._recv_count.get(w, 0) < self._rounds:
+                self._recv_one(w)
+                self._recv_count[w] = self._recv_count.get(w, 0) + 1
+                dropped += 1
+        self._stale_dropped += dropped
+        return dropped
 
     # -- straggler kill signal (tag 77) -------------------------------------
     def send_kill(self, worker_rank: int, step: int = 0) -> None:

@@ -178,6 +178,8 @@ class FusedEngine:
                 self.t_ew_cnt = torch.tensor([cb + 256 * w for w in range(self.W)], dtype=torch.int64, device=dev)
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self.ps_grid = min(len(self.plan.ps_tiles), sm * 3)
+        max_cols = max([l.cols for l in self.plan.layers if l.route == P.ROUTE_SVD_TS] or [0])
+        self.eig_threads = 1024 if max_cols > 32 else 256
 
         # ---- metrics + static batch ----------------------------------------------------------
         self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)  # loss, prec1, prec5
@@ -247,7 +249,7 @@ class FusedEngine:
                 C.gram(self.flat_grads, self.t_layers, self.t_enc_tiles, len(pl.enc_tiles), self.gpart)
                 C.eig_sample(self.t_layers, self.t_ts_layers, self.gpart, self.vsel, self.selcount, self.sigma,
                              arena0, pl.arena_floats, self.ctrl, None, self.svd_rank, self.random_sample,
-                             self.waterfill, self.systematic, self.worker_index)
+                             self.waterfill, self.systematic, self.worker_index, self.eig_threads)
                 n += 2
             C.project_push(self.flat_grads, self.t_layers, self.t_enc_tiles, len(pl.enc_tiles), self.vsel,
                            self.selcount, arena0, pl.arena_floats, self.ps_push_flags, self.ctrl,

@@ -144,6 +144,14 @@ class SyncReplicasMaster_NN(NN_Trainer):
             gather_start = time.time()
             coded_msgs = self.comm.gather(self.cur_step, need=self._num_aggregate)
             gather_duration = time.time() - gather_start
+            if self._num_aggregate < self._num_workers:
+                # backup-worker mode: the update uses the first N arrivals; tell the stragglers to
+                # abandon the step (tag 77, lenet.py:173-180) and drop whatever they still send, so
+                # the collective broadcast of the next step cannot deadlock behind them
+                for w in range(1, self.world_size):
+                    if w not in coded_msgs and self._kwargs.get("kill_stragglers", False):
+                        self.comm.send_kill(w, self.cur_step)
+                self.comm.drain()
 
             decode_start = time.time()
             n_used = self._decode(coded_msgs)
@@ -159,6 +167,7 @@ class SyncReplicasMaster_NN(NN_Trainer):
                 self.shrink_counter += 1
                 self.lr = self._base_lr * self._lr_shrinkage ** self.shrink_counter
                 self.optimizer.set_lr(self.lr)  # the reference never did this (master:232-234)
+        self.comm.drain()
         self.comm.send_step(STOP_STEP)
 
     def async_bcast_step(self):

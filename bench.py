@@ -1,0 +1,236 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-18 / CIFAR-10-shaped synthetic images/sec through the
+fused NVLink parameter-server engine (BASELINE.json metric + config 2).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+           --master-port 29500 bench.py --gpus 8 --steps 50 --warmup 5
+
+Rank 0 prints ONE JSON line.  ``value`` is the whole-job images/s, timed on the
+device with CUDA events around exactly K steps (barrier + synchronize on both
+sides, max over ranks).  ``e2e`` repeats the measurement through the public
+``FusedEngine.train_step(x, y)`` API with the batch coming from pinned host
+memory every step and the loss read back to the host every step.
+
+``--impl reference`` reports the reference arm (not installable here: Python-2 /
+mpi4py / missing module — see DESIGN.md); ``--impl nccl-baseline`` runs the
+reference *algorithm* re-hosted on torch.distributed/NCCL + torch.linalg.svd
+(this repo's role classes), the bar BASELINE.md names.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ResNet-18 CIFAR-10 images/sec (whole box, device-timed, max over ranks)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="atomo_b200", choices=["atomo_b200", "reference", "nccl-baseline"])
+    ap.add_argument("--network", type=str, default="ResNet18")
+    ap.add_argument("--batch-size", type=int, default=128, help="per-worker batch (run_pytorch.sh: 128)")
+    ap.add_argument("--code", type=str, default="svd")
+    ap.add_argument("--svd-rank", type=int, default=3)
+    ap.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ps-mode", type=str, default="colocated", choices=["colocated", "dedicated"])
+    ap.add_argument("--sampling", type=str, default="bernoulli")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
+                    help="activations are NHWC by default (2.3x faster convs/BN on B200)")
+    ap.add_argument("--momentum", type=float, default=0.9)
+    ap.add_argument("--lr", type=float, default=0.01)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def reference_arm(args):
+    print(json.dumps({
+        "impl": "reference",
+        "unavailable": "hwang595/ATOMO has no setup.py/pyproject (pip: 'not installable'), is Python-2.7 + mpi4py + "
+                       "torch-0.3 and imports a module missing from its tree (codings.lossless_compress)"}))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    if args.impl == "nccl-baseline":
+        from baseline.nccl_ps import run_baseline
+        return run_baseline(args, rank, world, dev)
+
+    from atomo_b200.data import SyntheticImageDataset
+    from atomo_b200.models import build_model, input_shape
+    from atomo_b200.runtime.engine import FusedEngine
+
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = build_model(args.network, 10, "Cifar10")
+    eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
+                      ps_mode=args.ps_mode, sampling=args.sampling, dtype=args.dtype, channels_last=args.channels_last,
+                      use_graph=not args.no_graph, seed=1, timeout_s=60.0)
+    shape = input_shape(args.network, "Cifar10")
+    ds = SyntheticImageDataset(shape, 10, 50000, seed=rank)
+    nbatches = 8
+    xs, ys = ds.materialize(args.batch_size * nbatches)
+    host_x = [xs[i * args.batch_size:(i + 1) * args.batch_size].contiguous().pin_memory() for i in range(nbatches)]
+    host_y = [ys[i * args.batch_size:(i + 1) * args.batch_size].contiguous().pin_memory() for i in range(nbatches)]
+    torch.cuda.reset_peak_memory_stats(dev)
+    base_mem = torch.cuda.memory_allocated(dev)
+    eng.prepare(host_x[0], host_y[0], warmup=max(args.warmup, 3))
+    work_mb = (torch.cuda.max_memory_allocated(dev) - base_mem) / 2 ** 20 + 3 * eng.plan.total_elems * 4 / 2 ** 20
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nworkers = eng.W
+    imgs_per_step = nworkers * args.batch_size
+
+    # ---- device-timed: the step graph alone (inputs resident) ---------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.train_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.train_step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    value = imgs_per_step * args.steps / (ms / 1e3)
+
+    # ---- end to end: public API, pinned-host inputs every step, loss to the host every step ------
+    pinned_loss = torch.zeros(3, dtype=torch.float32).pin_memory()
+    for i in range(3):
+        eng.train_step(host_x[i % nbatches], host_y[i % nbatches])
+    barrier()
+    copy_evt = torch.cuda.Event()
+    losses = []
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        stats = eng.train_step(host_x[i % nbatches], host_y[i % nbatches])
+        if i > 0:
+            copy_evt.synchronize()          # previous step's loss has landed on the host
+            losses.append(float(pinned_loss[0]))
+        pinned_loss.copy_(stats, non_blocking=True)
+        copy_evt.record()
+    copy_evt.synchronize()
+    losses.append(float(pinned_loss[0]))
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e_value = imgs_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = host_x[0].numel() * host_x[0].element_size() + host_y[0].numel() * host_y[0].element_size()
+    err = eng.error_code()
+
+    if rank == 0:
+        par = ("ps+%dworkers(colocated)" % nworkers) if args.ps_mode == "colocated" else ("ps+%dworkers" % nworkers)
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "impl": "atomo_b200",
+            "config": {"model": args.network, "global_batch": imgs_per_step, "per_worker_batch": args.batch_size,
+                       "seq_len": None, "image": list(shape), "parallelism": par, "code": args.code,
+                       "svd_rank": args.svd_rank, "sampling": args.sampling, "cuda_graph": not args.no_graph,
+                       "heap": eng.heap.mode, "nvls_multicast": eng.heap.has_multicast,
+                       "l2": "no explicit flush: per-step working set %.0f MB > 126 MB L2" % work_mb,
+                       "optimizer": "momentum-SGD fused in PS kernel", "final_loss": round(losses[-1], 4),
+                       "device_error": err},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+            "gpu_launches": eng.launches_per_step * args.steps,
+        }
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+"""PS/worker plumbing on CPU: wire format, plan tables, gloo multi-process runs, checkpoints, evaluator, parser."""
+import os
+import struct
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from atomo_b200 import codings
+from atomo_b200.ops import plan as P
+from atomo_b200.parallel import wire
+from atomo_b200.utils import checkpoint as ckpt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_wire_roundtrip_all_coders():
+    g = torch.randn(12, 6, 3, 3)
+    msgs = [codings.build(n, **kw).encode(g) for n, kw in
+            [("svd", dict(rank=2)), ("qsgd", {}), ("entrywise", dict(budget=0.2)), ("sgd", {}),
+             ("sgd", dict(compress=True)), ("qsvd", dict(rank=2))]]
+    buf = wire.pack({"step": 9, "rank": 1, "codes": msgs})
+    assert buf.dtype == torch.uint8
+    out = wire.unpack(buf)
+    assert out["step"] == 9 and len(out["codes"]) == len(msgs)
+    for name, a, b in zip(["svd", "qsgd", "entrywise", "sgd", "sgd", "qsvd"], msgs, out["codes"]):
+        coder = codings.build(name, rank=2) if name in ("svd", "qsvd") else codings.build(name)
+        assert torch.allclose(coder.decode(a), coder.decode(b))
+    with pytest.raises(ValueError):
+        wire.unpack(torch.zeros(64, dtype=torch.uint8))
+
+
+def test_plan_tables_resnet18():
+    from atomo_b200.models import build_model
+    from atomo_b200.runtime.flat import FlatLayout
+    m = build_model("ResNet18")
+    lay = FlatLayout.from_module(m)
+    pl = P.build_plan(lay.shapes, "svd", 3, offsets=lay.offsets)
+    assert pl.total_elems == lay.total
+    ts = [l for l in pl.layers if l.route == P.ROUTE_SVD_TS]
+    assert len(ts) == 18  # 17 3x3 convs + fc (transposed); the square-ish 1x1 shortcuts travel dense
+    conv = next(l for l in ts if l.shape == (512, 512, 3, 3))
+    assert (conv.rows, conv.cols, conv.row_stride, conv.col_stride) == (131072, 18, 18, 1)
+    fc = next(l for l in ts if l.shape == (10, 512))
+    assert (fc.rows, fc.cols, fc.row_stride, fc.col_stride) == (512, 10, 1, 512)
+    assert all(l.route == P.ROUTE_DENSE for l in pl.layers if len(l.shape) == 1)
+    # tiles cover every row / element exactly once
+    for l in ts:
+        rows = sum(t[2] for t in pl.enc_tiles if t[0] == l.index)
+        assert rows == l.rows
+        rows = sum(t[2] for t in pl.ps_tiles if t[0] == l.index)
+        assert rows == l.rows
+        assert l.ps_rows * l.cols <= P.PS_TILE_ELEMS and l.ps_rows * ((l.cols + 3) // 4) <= 1024
+        assert l.slot_off % 32 == 0 and P.slot_u_off(l.rcap, l.cols) % 4 == 0
+    for l in pl.layers:
+        if l.route == P.ROUTE_DENSE:
+            assert sum(t[2] for t in pl.ps_tiles if t[0] == l.index) == l.numel
+    assert len(pl.layers_bytes()) == 72 * 62 and P.CTRL_BYTES == 56
+    step, err, lr = struct.unpack_from("<iif", P.pack_ctrl(step=4, lr=0.5))
+    assert (step, err) == (4, 0) and lr == 0.5
+    # r=3 factors are several times smaller than the dense gradient (~6x at the reference's sizes)
+    assert pl.factor_bytes_per_worker() < 0.5 * 4 * lay.total
+
+
+def test_slot_capacity_rules():
+    assert P.slot_capacity(18, 3, False) == 8 and P.slot_capacity(18, 3, True) == 4
+    assert P.slot_capacity(2, 3, False) == 4 and P.slot_capacity(50, 16, False) == 32
+    assert P.slot_capacity(18, 0, False) == 20
+
+
+def test_checkpoint_layout_and_resume(tmp_path):
+    net = torch.nn.Linear(4, 2)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    d = str(tmp_path) + "/"
+    path = ckpt.save_model(d, 50, net)
+    assert path == d + "model_step_50" and os.path.isfile(path)  # master:331-336 naming
+    ckpt.save_sidecar(d, 50, opt, lr=0.05, extra={"shrink_counter": 1})
+    ckpt.save_model(d, 100, net)
+    assert ckpt.latest_step(d) == 100
+    net2 = torch.nn.Linear(4, 2)
+    ckpt.load_model(d, 50, net2)
+    assert torch.equal(net2.weight, net.weight)
+    side = ckpt.load_sidecar(d, 50, opt)
+    assert side["lr"] == 0.05 and side["step"] == 50 and side["shrink_counter"] == 1
+    assert ckpt.load_sidecar(d, 100) is None
+
+
+def _run_launcher(extra, timeout=240):
+    cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
+           "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64"] + extra
+    env = dict(os.environ, ATOMO_HANG_DUMP_S=str(timeout - 20), PYTHONPATH=ROOT)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_baseline_config1_lenet_entrywise_gloo_world2(tmp_path):
+    """BASELINE.json config 1: LeNet, MNIST-shaped synthetic, entry-wise sparsifier, PS + 1 worker on CPU/gloo."""
+    from atomo_b200.tiny_tuning_parser import parse_line
+    d = str(tmp_path) + "/"
+    out = _run_launcher(["--nproc", "2", "--network", "LeNet", "--dataset", "MNIST", "--code", "entrywise",
+                         "--entry-budget", "0.1", "--max-steps", "8", "--eval-freq", "4", "--train-dir", d,
+                         "--master-port", "29541"])
+    recs = [parse_line(l) for l in out.splitlines() if l.startswith("Worker:")]
+    assert len(recs) == 8 and all(r is not None for r in recs)
+    assert recs[-1]["loss"] < recs[0]["loss"]
+    assert recs[0]["msg_mb"] < 0.5  # 10% of 1.64 MiB (x2 for indices)
+    assert "Master: Step: 8" in out and "Test set: Step: 4" in out
+    assert os.path.isfile(d + "model_step_4") and os.path.isfile(d + "model_step_8_optim")
+    # the polling evaluator consumes the same files (distributed_evaluator.py contract)
+    from atomo_b200.distributed_evaluator import main as ev_main
+    res = ev_main(["--model-dir", d, "--eval-freq", "4", "--network", "LeNet", "--dataset", "MNIST", "--synthetic", "1",
+                   "--test-len", "128", "--eval-batch-size", "64", "--max-evals", "2", "--poll-seconds", "0.1"])
+    assert [r["step"] for r in res] == [4, 8]
+
+
+@pytest.mark.parametrize("code,extra", [("svd", ["--svd-rank", "3"]), ("qsgd", ["--quantization-level", "4"]),
+                                        ("sgd", []), ("qsvd", ["--svd-rank", "2"])])
+def test_three_rank_gloo_all_coders(code, extra, tmp_path):
+    out = _run_launcher(["--nproc", "3", "--network", "LeNet", "--dataset", "MNIST", "--code", code,
+                         "--max-steps", "4", "--eval-freq", "100", "--train-dir", str(tmp_path) + "/",
+                         "--master-port", str(29550 + len(code) + len(extra))] + extra)
+    assert out.count("Worker: 1, Step:") == 4 and out.count("Worker: 2, Step:") == 4
+    assert "Master: Step: 4" in out
+
+
+def test_num_aggregate_backup_workers(tmp_path):
+    # PS proceeds after 1 of 2 gradients; stale messages are dropped, run still terminates cleanly
+    out = _run_launcher(["--nproc", "3", "--network", "LeNet", "--dataset", "MNIST", "--code", "sgd",
+                         "--max-steps", "5", "--num-aggregate", "1", "--eval-freq", "100",
+                         "--train-dir", str(tmp_path) + "/", "--master-port", "29571"])
+    assert "Master: Step: 5" in out
+
+
+def test_resume_continues_from_checkpoint(tmp_path):
+    d = str(tmp_path) + "/"
+    common = ["--nproc", "2", "--network", "LeNet", "--dataset", "MNIST", "--code", "sgd", "--eval-freq", "3",
+              "--train-dir", d]
+    _run_launcher(common + ["--max-steps", "3", "--master-port", "29581"])
+    out = _run_launcher(common + ["--max-steps", "5", "--resume", "1", "--master-port", "29582"])
+    assert "Master: Step: 4" in out and "Master: Step: 3," not in out
+
+
+def test_single_machine_and_tuning_parser(tmp_path):
+    from atomo_b200.single_machine import main as sm_main
+    res = sm_main(["--network", "LeNet", "--dataset", "MNIST", "--synthetic", "1", "--train-len", "256", "--test-len",
+                   "64", "--batch-size", "32", "--max-steps", "6", "--test-batch-size", "64", "--lr", "0.05"])
+    assert res["loss"] > 0
+    from atomo_b200.tiny_tuning_parser import main as tp_main
+    from atomo_b200.utils.logging import worker_line
+    f = tmp_path / "0.01"
+    f.write_text("\n".join(worker_line(w, 100, 0, 0, 100, 1.0 + w, 0.1, 0.1, 0.1, 0.1, 1.0, 10, 50) for w in (1, 2, 3)))
+    assert tp_main(["--tuning-dir", str(tmp_path), "--tuning-lr", "0.01", "--num-workers", "3"]) == pytest.approx(3.0)
+
+
+def test_data_sharding_and_loader():
+    from atomo_b200.data import DataLoader, build_datasets, shard_indices
+    a, b = shard_indices(100, 0, 2, seed=3), shard_indices(100, 1, 2, seed=3)
+    assert len(set(a.tolist()) & set(b.tolist())) == 0 and len(a) == len(b) == 50
+    tr, te, nc = build_datasets("Cifar100", synthetic=True, train_len=64, test_len=16)
+    assert nc == 100 and tr[0][0].shape == (3, 32, 32)
+    ld = DataLoader(tr, batch_size=16, shuffle=True, prefetch=2)
+    for _ in range(6):  # wraps over the epoch boundary (persistent iterator, my_data_loader.py:310-319)
+        x, y = ld.next_batch()
+        assert x.shape == (16, 3, 32, 32)
+    assert ld.epochs_completed >= 1
+    ld.close()
