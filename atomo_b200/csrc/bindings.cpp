@@ -46,8 +46,9 @@ void atomo_launch_ps_update(const void* layers, const void* tiles, int ntiles, i
                             float* params, float* momentum, float* const* params_peer, float* params_mc,
                             const float* const* grads_peer, const float* grads_mc, const float* arenas,
                             long long arena_floats, int* push_flags, int* const* param_flag_peer, void* ctrl,
-                            long long timeout_ticks, float inv_w, int grid, cudaStream_t stream);
-void atomo_launch_wait_params(const int* param_flag, void* ctrl, long long timeout_ticks, cudaStream_t stream);
+                            long long timeout_ticks, float inv_w, int grid, long long* tstats, cudaStream_t stream);
+void atomo_launch_wait_params(const int* param_flag, void* ctrl, long long timeout_ticks, long long* tstats,
+                              cudaStream_t stream);
 void atomo_launch_advance_step(void* ctrl, cudaStream_t stream);
 void atomo_launch_param_bcast(const float* src, float* const* params_peer, float* params_mc, int nranks,
                               int self_rank, long long numel, cudaStream_t stream);
@@ -152,7 +153,7 @@ void ps_update(const torch::Tensor& layers, const torch::Tensor& tiles, int ntil
                torch::Tensor params, torch::Tensor momentum, const torch::Tensor& params_peer, uint64_t params_mc,
                const torch::Tensor& grads_peer, uint64_t grads_mc, uint64_t arenas, int64_t arena_floats,
                uint64_t push_flags, const torch::Tensor& param_flag_peer, torch::Tensor ctrl,
-               int64_t timeout_ticks, double inv_w, int grid) {
+               int64_t timeout_ticks, double inv_w, int grid, uint64_t tstats) {
   check_cuda_f32(params, "params");
   check_cuda_f32(momentum, "momentum");
   TORCH_CHECK(W <= atomo_ps_max_workers(), "too many workers for ps_update");
@@ -162,12 +163,13 @@ void ps_update(const torch::Tensor& layers, const torch::Tensor& tiles, int ntil
                          P<float>(params_mc), reinterpret_cast<const float* const*>(grads_peer.data_ptr()),
                          P<const float>(grads_mc), P<const float>(arenas), arena_floats, P<int>(push_flags),
                          reinterpret_cast<int* const*>(param_flag_peer.data_ptr()), ctrl.data_ptr(), timeout_ticks,
-                         (float)inv_w, grid, cur_stream());
+                         (float)inv_w, grid, P<long long>(tstats), cur_stream());
 }
 
-void wait_params(uint64_t param_flag, torch::Tensor ctrl, int64_t timeout_ticks) {
+void wait_params(uint64_t param_flag, torch::Tensor ctrl, int64_t timeout_ticks, uint64_t tstats) {
   c10::cuda::CUDAGuard guard(ctrl.device());
-  atomo_launch_wait_params(P<const int>(param_flag), ctrl.data_ptr(), timeout_ticks, cur_stream());
+  atomo_launch_wait_params(P<const int>(param_flag), ctrl.data_ptr(), timeout_ticks, P<long long>(tstats),
+                           cur_stream());
 }
 void advance_step(torch::Tensor ctrl) {
   c10::cuda::CUDAGuard guard(ctrl.device());
@@ -260,8 +262,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("systematic"), py::arg("worker_index"), py::arg("threads") = 256);
   m.def("project_push", &project_push);
   m.def("signal_push", &signal_push);
-  m.def("ps_update", &ps_update);
-  m.def("wait_params", &wait_params);
+  m.def("ps_update", &ps_update, py::arg("layers"), py::arg("tiles"), py::arg("ntiles"), py::arg("W"),
+        py::arg("nflags"), py::arg("nranks"), py::arg("params"), py::arg("momentum"), py::arg("params_peer"),
+        py::arg("params_mc"), py::arg("grads_peer"), py::arg("grads_mc"), py::arg("arenas"),
+        py::arg("arena_floats"), py::arg("push_flags"), py::arg("param_flag_peer"), py::arg("ctrl"),
+        py::arg("timeout_ticks"), py::arg("inv_w"), py::arg("grid"), py::arg("tstats") = 0);
+  m.def("wait_params", &wait_params, py::arg("param_flag"), py::arg("ctrl"), py::arg("timeout_ticks"),
+        py::arg("tstats") = 0);
   m.def("advance_step", &advance_step);
   m.def("param_bcast", &param_bcast);
   m.def("set_flags", &set_flags);

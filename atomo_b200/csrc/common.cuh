@@ -146,6 +146,12 @@ __device__ __forceinline__ float4 multimem_ld_reduce_f4(const float4* mc) {
   return v;
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Bounded spin on a step-stamped flag written by a peer GPU.  Returns false on
 // timeout (caller records an error instead of hanging the GPU forever).
 __device__ __forceinline__ bool spin_wait_ge(const int* flag, int want, long long max_ns) {

@@ -52,6 +52,7 @@ struct PsArgs {
   Ctrl* ctrl;
   long long timeout_ticks;
   float inv_w;                    // 1 / (number of gradients averaged)
+  long long* tstats;              // optional device stats: [0] sum ns waiting for pushes, [1] sum ns working, [2] steps
 };
 
 __device__ __forceinline__ void sgd_update(float g, float& p, float& m, const float lr, const float mu,
@@ -87,6 +88,8 @@ ps_update_kernel(PsArgs a) {
   float* SV = OUT + PS_TILE_ELEMS;                       // PS_KC x 64
   float* UT = SV + PS_KC * TS_MAX_COLS;                  // PS_MAX_ROWS x (PS_KC+1)
   __shared__ int cnt[PS_MAX_W], koff[PS_MAX_W + 1];
+  __shared__ int grp_w[PS_MAX_W * RCAP_MAX / 4], grp_a0[PS_MAX_W * RCAP_MAX / 4];
+  __shared__ int s_ngrp;
   __shared__ int s_ok;
 
   const int tid = threadIdx.x;
@@ -94,11 +97,14 @@ ps_update_kernel(PsArgs a) {
   const int step = ctrl->step;
 
   // ---- 1. wait for every worker's push of this step ------------------------------------
+  long long t_enter = 0, t_ready = 0;
   if (tid == 0) {
+    t_enter = globaltimer_ns();
     bool ok = true;
     for (int w = 0; w < a.nflags; ++w) ok = spin_wait_ge(a.push_flags + w, step, a.timeout_ticks) && ok;
     if (!ok) atomicExch(&ctrl->error, ERR_WAIT_PUSH_TIMEOUT);
     s_ok = ok ? 1 : 0;
+    t_ready = globaltimer_ns();
   }
   __syncthreads();
   const bool ok = s_ok != 0;
@@ -108,7 +114,13 @@ ps_update_kernel(PsArgs a) {
   const bool first = (step == ctrl->first_step);
   const float inv_w = a.inv_w;
 
-  for (int ti = blockIdx.x; ok && ti < a.ntiles; ti += gridDim.x) {
+  // contiguous tile ranges per CTA: consecutive tiles mostly belong to the same layer, so the
+  // per-layer factor table (counts, S*V) is staged once and reused
+  const int per_cta = (a.ntiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per_cta;
+  const int t_end = min(a.ntiles, t_begin + per_cta);
+  int cached_layer = -1, cached_col0 = -1;
+  for (int ti = t_begin; ok && ti < t_end; ++ti) {
     const TileDesc t = a.tiles[ti];
     const LayerDesc L = a.layers[t.layer];
 
@@ -158,21 +170,30 @@ ps_update_kernel(PsArgs a) {
     const int ncp = nc4 << 2;
     const int rows = t.nrows;
     const int rcap = L.rcap;
+    const bool same = (t.layer == cached_layer && col0 == cached_col0);
 
     __syncthreads();  // previous tile fully consumed shared memory
-    if (tid < a.W) {
-      const int* hdr = reinterpret_cast<const int*>(a.arenas + (long long)tid * a.arena_floats + L.slot_off);
-      int c = ld_cg_i(hdr);
-      cnt[tid] = min(max(c, 0), rcap);
+    if (!same) {
+      if (tid < a.W) {
+        const int* hdr = reinterpret_cast<const int*>(a.arenas + (long long)tid * a.arena_floats + L.slot_off);
+        int c = ld_cg_i(hdr);
+        cnt[tid] = min(max(c, 0), rcap);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int k = 0, g = 0;
+        for (int w = 0; w < a.W; ++w) {
+          koff[w] = k; k += cnt[w];
+          for (int a0 = 0; a0 < cnt[w]; a0 += 4) { grp_w[g] = w; grp_a0[g] = a0; ++g; }
+        }
+        koff[a.W] = k;
+        s_ngrp = g;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (tid == 0) {
-      int k = 0;
-      for (int w = 0; w < a.W; ++w) { koff[w] = k; k += cnt[w]; }
-      koff[a.W] = k;
-    }
-    __syncthreads();
     const int K = koff[a.W];
+    const int NG = s_ngrp;
+    const bool single = K <= PS_KC;
 
     // accumulators: items (row, 4-column group); up to 4 items per thread
     const int items = rows * nc4;
@@ -182,28 +203,37 @@ ps_update_kernel(PsArgs a) {
 
     for (int k0 = 0; k0 < K; k0 += PS_KC) {
       const int kc = min(PS_KC, K - k0);
-      __syncthreads();
-      // SV[k][c] = s_w[a] * V_w[a][col0 + c]
-      for (int e = tid; e < kc * ncp; e += blockDim.x) {
-        const int k = e / ncp, c = e - k * ncp;
-        const int kk = k0 + k;
-        int w = 0;
-        while (kk >= koff[w + 1]) ++w;
-        const int at = kk - koff[w];
-        const float* slot = a.arenas + (long long)w * a.arena_floats + L.slot_off;
-        float v = 0.f;
-        if (c < nc) v = ld_cg_f(slot + slot_s_off() + at) * ld_cg_f(slot + slot_v_off(rcap) + (long long)at * n + col0 + c);
-        SV[k * TS_MAX_COLS + c] = v;
+      if (k0 > 0) __syncthreads();
+      // SV[k][c] = s_w[a] * V_w[a][col0 + c]   (kept across tiles of the same layer when K fits one chunk)
+      if (!(same && single)) {
+        for (int e = tid; e < kc * ncp; e += blockDim.x) {
+          const int k = e / ncp, c = e - k * ncp;
+          const int kk = k0 + k;
+          int w = 0;
+          while (kk >= koff[w + 1]) ++w;
+          const int at = kk - koff[w];
+          const float* slot = a.arenas + (long long)w * a.arena_floats + L.slot_off;
+          float v = 0.f;
+          if (c < nc) v = ld_cg_f(slot + slot_s_off() + at) * ld_cg_f(slot + slot_v_off(rcap) + (long long)at * n + col0 + c);
+          SV[k * TS_MAX_COLS + c] = v;
+        }
       }
-      // UT[r][k] = U_w[row0 + r][a]
-      for (int e = tid; e < rows * kc; e += blockDim.x) {
-        const int r = e / kc, k = e - r * kc;
-        const int kk = k0 + k;
-        int w = 0;
-        while (kk >= koff[w + 1]) ++w;
-        const int at = kk - koff[w];
+      // UT[r][k] = U_w[row0 + r][a]: one 16-byte load per (row, worker, 4-atom group)
+      for (int e = tid; e < rows * NG; e += blockDim.x) {
+        const int r = e / NG, g = e - r * NG;
+        const int w = grp_w[g], a0 = grp_a0[g];
+        const int kbase = koff[w] + a0 - k0;   // position of atom a0 inside this chunk
+        if (kbase >= kc || kbase + 4 <= 0) continue;
         const float* U = a.arenas + (long long)w * a.arena_floats + L.slot_off + slot_u_off(rcap, n);
-        UT[r * (PS_KC + 1) + k] = ld_cg_f(U + (long long)(t.row0 + r) * rcap + at);
+        const float4 u4 = ld_cg_f4(reinterpret_cast<const float4*>(U + (long long)(t.row0 + r) * rcap + a0));
+        const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
+        const int lim = cnt[w] - a0;  // atoms of this group that exist
+        float* dst = &UT[r * (PS_KC + 1)];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kbase + j;
+          if (j < lim && k >= 0 && k < kc) dst[k] = uv[j];
+        }
       }
       __syncthreads();
 #pragma unroll
@@ -221,6 +251,8 @@ ps_update_kernel(PsArgs a) {
         }
       }
     }
+    cached_layer = single ? t.layer : -1;
+    cached_col0 = col0;
     __syncthreads();
     // stage the averaged gradient tile: OUT[r*nc + c]
 #pragma unroll
@@ -285,14 +317,21 @@ ps_update_kernel(PsArgs a) {
       ctrl->done_ps = 0;
       __threadfence_system();
       for (int r = 0; r < a.nranks; ++r) st_release_sys(a.param_flag_peer[r], step + 1);
+      if (a.tstats != nullptr) {  // the last CTA to finish closes the books for this step
+        a.tstats[0] += t_ready - t_enter;
+        a.tstats[1] += globaltimer_ns() - t_ready;
+        a.tstats[2] += 1;
+      }
     }
   }
 }
 
 // worker side of K9: block the stream until the PS has delivered the parameters of `step`
-__global__ void wait_params_kernel(const int* param_flag, Ctrl* ctrl, long long timeout_ticks) {
+__global__ void wait_params_kernel(const int* param_flag, Ctrl* ctrl, long long timeout_ticks, long long* tstats) {
   if (threadIdx.x == 0) {
+    const long long t0 = globaltimer_ns();
     if (!spin_wait_ge(param_flag, ctrl->step, timeout_ticks)) atomicExch(&ctrl->error, ERR_WAIT_PARAM_TIMEOUT);
+    if (tstats != nullptr) { tstats[3] += globaltimer_ns() - t0; tstats[4] += 1; }
   }
 }
 
@@ -336,7 +375,7 @@ void atomo_launch_ps_update(const void* layers, const void* tiles, int ntiles, i
                             float* momentum, float* const* params_peer, float* params_mc,
                             const float* const* grads_peer, const float* grads_mc, const float* arenas,
                             long long arena_floats, int* push_flags, int* const* param_flag_peer, void* ctrl,
-                            long long timeout_ticks, float inv_w, int grid, cudaStream_t stream) {
+                            long long timeout_ticks, float inv_w, int grid, long long* tstats, cudaStream_t stream) {
   static bool attr_set = false;
   const int smem = atomo_ps_smem_bytes();
   if (!attr_set) {
@@ -349,13 +388,14 @@ void atomo_launch_ps_update(const void* layers, const void* tiles, int ntiles, i
   a.nranks = nranks; a.params = params; a.momentum = momentum; a.params_peer = params_peer;
   a.params_mc = params_mc; a.grads_peer = grads_peer; a.grads_mc = grads_mc; a.arenas = arenas;
   a.arena_floats = arena_floats; a.push_flags = push_flags; a.param_flag_peer = param_flag_peer;
-  a.ctrl = (Ctrl*)ctrl; a.timeout_ticks = timeout_ticks; a.inv_w = inv_w;
+  a.ctrl = (Ctrl*)ctrl; a.timeout_ticks = timeout_ticks; a.inv_w = inv_w; a.tstats = tstats;
   if (grid < 1) grid = 1;
   ps_update_kernel<<<grid, PS_THREADS, smem, stream>>>(a);
 }
 
-void atomo_launch_wait_params(const int* param_flag, void* ctrl, long long timeout_ticks, cudaStream_t stream) {
-  wait_params_kernel<<<1, 32, 0, stream>>>(param_flag, (Ctrl*)ctrl, timeout_ticks);
+void atomo_launch_wait_params(const int* param_flag, void* ctrl, long long timeout_ticks, long long* tstats,
+                              cudaStream_t stream) {
+  wait_params_kernel<<<1, 32, 0, stream>>>(param_flag, (Ctrl*)ctrl, timeout_ticks, tstats);
 }
 
 void atomo_launch_advance_step(void* ctrl, cudaStream_t stream) {

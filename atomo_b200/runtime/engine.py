@@ -183,6 +183,9 @@ class FusedEngine:
 
         # ---- metrics + static batch ----------------------------------------------------------
         self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)  # loss, prec1, prec5
+        # device-side phase accounting (globaltimer ns): [0] PS wait-for-pushes, [1] PS work, [2] PS steps,
+        # [3] wait-for-params, [4] steps
+        self.tstats = torch.zeros(8, dtype=torch.int64, device=dev)
         self.static_x = None
         self.static_y = None
         self.graph = None
@@ -213,6 +216,17 @@ class FusedEngine:
     def set_lr(self, lr: float):
         self.lr = lr
         self.ctrl_f32[2] = lr  # Ctrl::lr (device write ordered on the stream)
+
+    def phase_stats(self, reset: bool = True) -> dict:
+        """Average device-side microseconds per step since the last reset."""
+        t = self.tstats.tolist()
+        out = {"param_wait_us": t[3] / max(t[4], 1) / 1e3}
+        if self.is_ps:
+            out["ps_wait_push_us"] = t[0] / max(t[2], 1) / 1e3
+            out["ps_work_us"] = t[1] / max(t[2], 1) / 1e3
+        if reset:
+            self.tstats.zero_()
+        return out
 
     def error_code(self) -> int:
         return int(self.ctrl_i32[1].item())
@@ -291,7 +305,7 @@ class FusedEngine:
             C.ps_update(self.t_layers, self.t_ps_tiles, len(pl.ps_tiles), self.W, self.W, self.world,
                         self.flat_params, self.momentum_buf, self.t_params_peer, self.params_mc, self.t_grads_peer,
                         self.grads_mc, arenas, pl.arena_floats, self.ps_push_flags, self.t_flag_peer, self.ctrl,
-                        self.timeout_ticks, 1.0 / self.W, self.ps_grid)
+                        self.timeout_ticks, 1.0 / self.W, self.ps_grid, self.tstats.data_ptr())
             return 1
         if self.code in ("qsgd", "terngrad"):
             C.qsgd_decode_sum(self.t_qwords, self.t_qnorms, self.W, pl.total_elems, self.bucket, self.q,
@@ -306,14 +320,14 @@ class FusedEngine:
         C.ps_update(self.t_dense_layers, self.t_dense_ps_tiles, len(dp.ps_tiles), 1, 0, self.world,
                     self.flat_params, self.momentum_buf, self.t_params_peer, self.params_mc, self.t_out_sum_ptr, 0,
                     0, dp.arena_floats, self.ps_push_flags, self.t_flag_peer, self.ctrl, self.timeout_ticks,
-                    1.0 / self.W, min(len(dp.ps_tiles), self.ps_grid))
+                    1.0 / self.W, min(len(dp.ps_tiles), self.ps_grid), self.tstats.data_ptr())
         return n + 1
 
     def _step_body(self):
         """One full step on the current stream (capturable)."""
         C = self.C
         n = 0
-        C.wait_params(self.local_param_flag, self.ctrl, self.timeout_ticks); n += 1
+        C.wait_params(self.local_param_flag, self.ctrl, self.timeout_ticks, self.tstats.data_ptr()); n += 1
         if self.is_worker:
             self.flat_grads.zero_()
             self._forward_backward()

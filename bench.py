@@ -170,6 +170,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.train_step()
     barrier()
+    eng.phase_stats(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -181,6 +182,8 @@ def main():
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
     value = imgs_per_step * args.steps / (ms / 1e3)
+    phases = eng.phase_stats(reset=True)
+    phases["param_wait_us_max"] = max_over_ranks(phases["param_wait_us"])
 
     # ---- end to end: public API, pinned-host inputs every step, loss to the host every step ------
     pinned_loss = torch.zeros(3, dtype=torch.float32).pin_memory()
@@ -225,6 +228,7 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
             "gpu_launches": eng.launches_per_step * args.steps,
+            "phase_us": {k: round(v, 1) for k, v in phases.items()},
         }
         print(json.dumps(out))
     eng.close()
