@@ -53,6 +53,15 @@ void atomo_launch_advance_step(void* ctrl, cudaStream_t stream);
 void atomo_launch_param_bcast(const float* src, float* const* params_peer, float* params_mc, int nranks,
                               int self_rank, long long numel, cudaStream_t stream);
 void atomo_launch_set_flags(int* const* flag_peer, int nranks, int value, cudaStream_t stream);
+// gemm_kernels.cu
+int atomo_gemm_tile_bytes();
+int atomo_gemm_smem_bytes();
+void atomo_launch_skinny_gemm(const void* tiles, int ntiles, void* ctrl, int grid, cudaStream_t stream);
+// ext_kernels.cu
+void atomo_launch_ext_finalize(const void* descs, const void* tiles, int ntiles, const float* arena_y,
+                               const float* arena_b, float* ps_arena_peer, long long arena_floats,
+                               const void* ctrl, int worker_index, cudaStream_t stream);
+int atomo_ext_desc_bytes();
 // qsgd_kernels.cu / entrywise_kernels.cu
 void atomo_launch_qsgd_encode(const float* grad, long long numel, int bucket, int q, int terngrad,
                               const float* clip_ptr, unsigned long long* words_out, float* norms_out,
@@ -146,6 +155,21 @@ void project_push(const torch::Tensor& grad, const torch::Tensor& layers, const 
 void signal_push(uint64_t push_flag_peer, const torch::Tensor& ctrl, int worker_index) {
   c10::cuda::CUDAGuard guard(ctrl.device());
   atomo_launch_signal_push(P<int>(push_flag_peer), ctrl.data_ptr(), worker_index, cur_stream());
+}
+
+void skinny_gemm(const torch::Tensor& tiles, int ntiles, torch::Tensor ctrl, int grid) {
+  c10::cuda::CUDAGuard guard(tiles.device());
+  atomo_launch_skinny_gemm(tiles.data_ptr(), ntiles, ctrl.data_ptr(), grid, cur_stream());
+}
+
+void ext_finalize(const torch::Tensor& descs, const torch::Tensor& tiles, int ntiles, const torch::Tensor& arena_y,
+                  const torch::Tensor& arena_b, uint64_t ps_arena_peer, int64_t arena_floats,
+                  const torch::Tensor& ctrl, int worker_index) {
+  check_cuda_f32(arena_y, "arena_y");
+  c10::cuda::CUDAGuard guard(arena_y.device());
+  atomo_launch_ext_finalize(descs.data_ptr(), tiles.data_ptr(), ntiles, arena_y.data_ptr<float>(),
+                            arena_b.data_ptr<float>(), P<float>(ps_arena_peer), arena_floats, ctrl.data_ptr(),
+                            worker_index, cur_stream());
 }
 
 // ---------------------------------------------------------------------------------------------- PS
@@ -262,6 +286,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("systematic"), py::arg("worker_index"), py::arg("threads") = 256);
   m.def("project_push", &project_push);
   m.def("signal_push", &signal_push);
+  m.def("ext_finalize", &ext_finalize);
+  m.def("skinny_gemm", &skinny_gemm);
+  m.def("gemm_tile_bytes", &atomo_gemm_tile_bytes);
+  m.def("gemm_smem_bytes", &atomo_gemm_smem_bytes);
+  m.def("ext_desc_bytes", &atomo_ext_desc_bytes);
   m.def("ps_update", &ps_update, py::arg("layers"), py::arg("tiles"), py::arg("ntiles"), py::arg("W"),
         py::arg("nflags"), py::arg("nranks"), py::arg("params"), py::arg("momentum"), py::arg("params_peer"),
         py::arg("params_mc"), py::arg("grads_peer"), py::arg("grads_mc"), py::arg("arenas"),

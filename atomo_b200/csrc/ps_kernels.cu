@@ -271,7 +271,7 @@ ps_update_kernel(PsArgs a) {
     __syncthreads();
 
     // fused optimizer epilogue + parameter broadcast
-    if (L.vec_ok && nc == n) {
+    if (L.vec_ok == 1 && nc == n) {
       // the tile is one contiguous, 16-byte aligned run of rows*n floats
       const long long e0 = L.off + (long long)t.row0 * n;
       const int nvec = (rows * n) >> 2;
@@ -293,6 +293,38 @@ ps_update_kernel(PsArgs a) {
         sgd_update(OUT[i], p, m, lr, mu, damp, wd, nesterov, first);
         a.momentum[e] = m;
         bcast_store1(a, e, p);
+      }
+    } else if (L.vec_ok == 2 && (nc & 3) == 0) {
+      // column-tiled wide layer: every row segment [col0, col0+nc) is contiguous and 16-byte aligned
+      const int q4 = nc >> 2;
+      for (int i = tid; i < rows * q4; i += blockDim.x) {
+        const int r = i / q4, c4 = i - r * q4;
+        const long long e = L.off + (long long)(t.row0 + r) * L.row_stride + col0 + 4 * c4;
+        const float4 g = *reinterpret_cast<const float4*>(&OUT[r * nc + 4 * c4]);
+        float4 p = *reinterpret_cast<float4*>(a.params + e);
+        float4 m = *reinterpret_cast<float4*>(a.momentum + e);
+        sgd_update(g.x, p.x, m.x, lr, mu, damp, wd, nesterov, first);
+        sgd_update(g.y, p.y, m.y, lr, mu, damp, wd, nesterov, first);
+        sgd_update(g.z, p.z, m.z, lr, mu, damp, wd, nesterov, first);
+        sgd_update(g.w, p.w, m.w, lr, mu, damp, wd, nesterov, first);
+        *reinterpret_cast<float4*>(a.momentum + e) = m;
+        bcast_store4(a, e, p);
+      }
+    } else if (L.vec_ok == 3 && (rows & 3) == 0 && (t.row0 & 3) == 0) {
+      // transposed orientation: memory is contiguous along the tall rows
+      const int r4n = rows >> 2;
+      for (int i = tid; i < nc * r4n; i += blockDim.x) {
+        const int c = i / r4n, r4 = i - c * r4n;
+        const long long e = L.off + (long long)(t.row0 + 4 * r4) * L.row_stride + (long long)(col0 + c) * L.col_stride;
+        const float* o = &OUT[(4 * r4) * nc + c];
+        float4 p = *reinterpret_cast<float4*>(a.params + e);
+        float4 m = *reinterpret_cast<float4*>(a.momentum + e);
+        sgd_update(o[0], p.x, m.x, lr, mu, damp, wd, nesterov, first);
+        sgd_update(o[nc], p.y, m.y, lr, mu, damp, wd, nesterov, first);
+        sgd_update(o[2 * nc], p.z, m.z, lr, mu, damp, wd, nesterov, first);
+        sgd_update(o[3 * nc], p.w, m.w, lr, mu, damp, wd, nesterov, first);
+        *reinterpret_cast<float4*>(a.momentum + e) = m;
+        bcast_store4(a, e, p);
       }
     } else {
       for (int i = tid; i < rows * nc; i += blockDim.x) {

@@ -381,7 +381,8 @@ eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ 
     float v = 0.f;
     if (a < count) {
       const int i = sel[a];
-      v = V[c * GS + i] / fmaxf(sig[i], 1e-20f);
+      // a (numerically) null direction has no left vector: emit a zero column instead of 1/0
+      v = (sig[i] > 1e-7f * sig[order[0]]) ? V[c * GS + i] / sig[i] : 0.f;
     }
     vs[e] = v;
   }

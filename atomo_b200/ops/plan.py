@@ -84,6 +84,8 @@ class Layer:
     ntiles: int = 0
     vec_ok: int = 0
     ps_rows: int = 0
+    sketch: int = 0      # ROUTE_LOWRANK_EXT: subspace width l
+    ext_index: int = -1
 
     def pack(self) -> bytes:
         return struct.pack(LAYER_FMT, self.off, self.slot_off, self.gpart_off, self.numel, self.rows, self.cols,
@@ -103,6 +105,7 @@ class Plan:
     gpart_floats: int
     code: str
     rank: int
+    ext: Optional["ExtPlan"] = None
 
     def layers_bytes(self) -> bytes:
         return b"".join(l.pack() for l in self.layers)
@@ -139,7 +142,8 @@ def _enc_rows_for(cols: int) -> int:
 
 
 def build_plan(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 3, systematic: bool = False,
-               dense_vectors: bool = True, offsets: Optional[Sequence[int]] = None) -> Plan:
+               dense_vectors: bool = True, offsets: Optional[Sequence[int]] = None, subspace: bool = False,
+               ext_min_numel: int = 16384) -> Plan:
     layers: List[Layer] = []
     off = 0
     for i, shape in enumerate(shapes):
@@ -157,11 +161,13 @@ def build_plan(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 3
             skinny = cols <= 32 or (cols <= TS_MAX_COLS and rows >= 8 * cols)
             if not (is_vector and dense_vectors) and cols >= 2 and rows >= cols and skinny:
                 route = ROUTE_SVD_TS
+            elif (not is_vector) and subspace and cols > 32 and numel >= ext_min_numel:
+                route = ROUTE_LOWRANK_EXT
         layers.append(Layer(i, shape, this_off, numel, rows, cols, rs, cs, route))
         off = this_off + _round_up(numel, ALIGN_ELEMS)
     total = max(off, ALIGN_ELEMS)
 
-    enc_tiles, ps_tiles, dense_tiles, ts_layers = [], [], [], []
+    enc_tiles, ps_tiles, dense_tiles, ts_layers, ext_layers = [], [], [], [], []
     slot_off, gpart_off = 0, 0
     for l in layers:
         if l.route == ROUTE_SVD_TS:
@@ -181,13 +187,106 @@ def build_plan(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 3
             l.ps_rows = _ps_rows_for(l.cols)
             for r0 in range(0, l.rows, l.ps_rows):
                 ps_tiles.append((l.index, r0, min(l.ps_rows, l.rows - r0), 0))
+        elif l.route == ROUTE_LOWRANK_EXT:
+            l.sketch = 16 if rank <= 6 else 32
+            l.rcap = slot_capacity(l.sketch, rank, systematic)
+            l.slot_off = slot_off
+            slot_off += slot_floats(l.rows, l.cols, l.rcap)
+            l.ext_index = len(ext_layers)
+            ext_layers.append(l)
+            # vectorised epilogue along whichever direction is contiguous in memory
+            if l.col_stride == 1:
+                l.vec_ok = 2 if (l.cols % 4 == 0 and l.row_stride % 4 == 0 and l.off % 4 == 0) else 0
+            else:
+                l.vec_ok = 3 if (l.row_stride == 1 and l.col_stride % 4 == 0 and l.off % 4 == 0) else 0
+            l.ps_rows = _ps_rows_for(TS_MAX_COLS)
+            for r0 in range(0, l.rows, l.ps_rows):
+                for c0 in range(0, l.cols, TS_MAX_COLS):
+                    ps_tiles.append((l.index, r0, min(l.ps_rows, l.rows - r0), c0))
         else:
             for e0 in range(0, l.numel, PS_DENSE_ELEMS):
                 ps_tiles.append((l.index, e0 // 4, min(PS_DENSE_ELEMS, l.numel - e0), 0))
         for e0 in range(0, l.numel, PS_DENSE_ELEMS):
             dense_tiles.append((l.index, e0 // 4, min(PS_DENSE_ELEMS, l.numel - e0), 0))
-    return Plan(layers, enc_tiles, ps_tiles, dense_tiles, ts_layers, total, max(slot_off, 32), max(gpart_off, 1),
+    plan = Plan(layers, enc_tiles, ps_tiles, dense_tiles, ts_layers, total, max(slot_off, 32), max(gpart_off, 1),
                 code, rank)
+    if ext_layers:
+        plan.ext = build_ext_plan(ext_layers, rank, systematic)
+    return plan
+
+
+# ----------------------------------------------------------------------------------------------
+# Subspace-iteration route (ROUTE_LOWRANK_EXT): square-ish layers (fc, 1x1 convs)
+# ----------------------------------------------------------------------------------------------
+EXT_FMT = "<8q8i"  # mirrors struct ExtDesc (96 bytes)
+EXT_BYTES = struct.calcsize(EXT_FMT)
+FIN_ROWS = 256
+
+
+@dataclass
+class ExtPlan:
+    """Scratch layout + auxiliary tall-skinny plans for the randomized range finder.
+
+    Per layer A (m x n, tall view):  Y = A X (m x l)  ->  Q = orth(Y)  ->  B = A^T Q (n x l)
+    ->  B = Ub S Vb^T  (complete SVD of the skinny B through the Gram/Jacobi kernels, atoms sampled
+    there)  ->  A ~ (Q Vb) S Ub^T.  ``aux_y`` / ``aux_b`` describe Y and B as tall-skinny "layers" of
+    a scratch buffer so the SAME gram / eig_sample / project kernels orthonormalise and factorise them.
+    """
+    layers: List[Layer]
+    descs: List[tuple]
+    aux_y: "Plan"
+    aux_b: "Plan"
+    scratch_floats: int
+    local_arena_floats: int
+    fin_tiles: List[Tuple[int, int, int, int]]
+
+    def descs_bytes(self) -> bytes:
+        return b"".join(struct.pack(EXT_FMT, *d) for d in self.descs)
+
+
+def _aux_plan(entries, rank, systematic, topk_all: bool) -> Plan:
+    """entries: (off, rows, cols, rcap). Builds a TS-only plan over a scratch buffer."""
+    layers, enc_tiles, ts_layers = [], [], []
+    slot_off = gpart_off = 0
+    for i, (off, rows, cols, rcap) in enumerate(entries):
+        l = Layer(i, (rows, cols), off, rows * cols, rows, cols, cols, 1, ROUTE_SVD_TS)
+        l.rcap = rcap
+        l.slot_off = slot_off
+        slot_off += slot_floats(rows, cols, rcap)
+        l.ts_index = i
+        ts_layers.append(i)
+        er = _enc_rows_for(cols)
+        l.tile0 = len(enc_tiles)
+        for r0 in range(0, rows, er):
+            enc_tiles.append((i, r0, min(er, rows - r0), 0))
+        l.ntiles = len(enc_tiles) - l.tile0
+        l.gpart_off = gpart_off
+        gpart_off += l.ntiles * cols * cols
+        layers.append(l)
+    total = max([l.off + l.numel for l in layers] + [ALIGN_ELEMS])
+    return Plan(layers, enc_tiles, [], [], ts_layers, total, max(slot_off, 32), max(gpart_off, 1), "svd", rank)
+
+
+def build_ext_plan(ext_layers: List[Layer], rank: int, systematic: bool) -> ExtPlan:
+    scratch = 0
+    descs, y_entries, b_entries, fin_tiles = [], [], [], []
+    for l in ext_layers:
+        sk = l.sketch
+        xt_off = scratch; scratch += _round_up(sk * l.cols, ALIGN_ELEMS)
+        y_off = scratch; scratch += _round_up(l.rows * sk, ALIGN_ELEMS)
+        b_off = scratch; scratch += _round_up(l.cols * sk, ALIGN_ELEMS)
+        y_entries.append((y_off, l.rows, sk, sk))        # orthonormalise: keep all l atoms
+        b_entries.append((b_off, l.cols, sk, l.rcap))    # factorise + sample
+        descs.append([l.off, xt_off, y_off, b_off, 0, 0, l.slot_off, 0,
+                      l.rows, l.cols, l.row_stride, l.col_stride, sk, l.rcap, l.index, 0])
+        for r0 in range(0, l.rows, FIN_ROWS):
+            fin_tiles.append((l.ext_index, r0, min(FIN_ROWS, l.rows - r0), 0))
+    aux_y = _aux_plan(y_entries, rank, systematic, True)
+    aux_b = _aux_plan(b_entries, rank, systematic, False)
+    for d, ly, lb in zip(descs, aux_y.layers, aux_b.layers):
+        d[4], d[5] = ly.slot_off, lb.slot_off  # Q slot / B slot inside their local arenas
+    return ExtPlan(ext_layers, [tuple(d) for d in descs], aux_y, aux_b, max(scratch, 32),
+                   aux_y.arena_floats + aux_b.arena_floats, fin_tiles)
 
 
 def dense_only_plan(shapes, offsets=None) -> Plan:

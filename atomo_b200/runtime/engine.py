@@ -53,7 +53,8 @@ class FusedEngine:
                  quantization_level: int = 4, bucket_size: int = 512, entry_budget: float = 0.05,
                  dtype: str = "fp32", channels_last: bool = False, use_graph: bool = True, group=None,
                  multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
-                 criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None):
+                 criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None,
+                 subspace: bool = True, power_iters: int = 0, gemm_impl: str = "auto"):
         self.C = load_ext()
         self.rank, self.world, self.group = rank, world, group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -86,7 +87,10 @@ class FusedEngine:
         self.layout = FlatLayout.from_module(self.model)
         shapes = self.layout.shapes
         plan_code = self.code if self.code == "svd" else "sgd"
-        self.plan = P.build_plan(shapes, plan_code, self.svd_rank, self.systematic, offsets=self.layout.offsets)
+        self.plan = P.build_plan(shapes, plan_code, self.svd_rank, self.systematic, offsets=self.layout.offsets,
+                                 subspace=subspace)
+        self.power_iters = int(power_iters)
+        self.gemm_impl = gemm_impl
         assert self.plan.total_elems == self.layout.total
         total = self.plan.total_elems
         nb = (total + self.bucket - 1) // self.bucket
@@ -176,6 +180,8 @@ class FusedEngine:
                 self.t_ew_idx = torch.tensor([ib + 4 * self.ew_capacity * w for w in range(self.W)], dtype=torch.int64, device=dev)
                 self.t_ew_val = torch.tensor([vb + 4 * self.ew_capacity * w for w in range(self.W)], dtype=torch.int64, device=dev)
                 self.t_ew_cnt = torch.tensor([cb + 256 * w for w in range(self.W)], dtype=torch.int64, device=dev)
+        if self.plan.ext is not None:
+            self._setup_ext()
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self.ps_grid = min(len(self.plan.ps_tiles), sm * 3)
         max_cols = max([l.cols for l in self.plan.layers if l.route == P.ROUTE_SVD_TS] or [0])
@@ -193,6 +199,129 @@ class FusedEngine:
         self._initial_sync()
 
     # ------------------------------------------------------------------------------------------
+    def _aux_tables(self, aux):
+        dev = self.device
+        n_ts = max(len(aux.ts_layers), 1)
+        return {
+            "plan": aux, "layers": _dev_bytes(aux.layers_bytes(), dev),
+            "tiles": _dev_bytes(P.Plan.tiles_bytes(aux.enc_tiles), dev),
+            "ts": torch.tensor(aux.ts_layers or [0], dtype=torch.int32, device=dev),
+            "gpart": torch.zeros(aux.gpart_floats, dtype=torch.float32, device=dev),
+            "vsel": torch.zeros(n_ts * P.TS_MAX_COLS * P.RCAP_MAX, dtype=torch.float32, device=dev),
+            "selcount": torch.zeros(n_ts, dtype=torch.int32, device=dev),
+            "arena": torch.zeros(aux.arena_floats, dtype=torch.float32, device=dev),
+        }
+
+    def _setup_ext(self):
+        """Scratch + auxiliary tables of the subspace-iteration route (square-ish layers)."""
+        ext, dev = self.plan.ext, self.device
+        self.ext_scratch = torch.zeros(ext.scratch_floats, dtype=torch.float32, device=dev)
+        self.aux_y = self._aux_tables(ext.aux_y)
+        self.aux_b = self._aux_tables(ext.aux_b)
+        self.t_ext_descs = _dev_bytes(ext.descs_bytes(), dev)
+        self.t_fin_tiles = _dev_bytes(P.Plan.tiles_bytes(ext.fin_tiles), dev)
+        assert self.C.ext_desc_bytes() == P.EXT_BYTES
+        self.ext_views = []
+        for l, d, ly in zip(ext.layers, ext.descs, ext.aux_y.layers):
+            a_off, xt_off, y_off, b_off, qslot_off = d[0], d[1], d[2], d[3], d[4]
+            sk = l.sketch
+            A = torch.as_strided(self.flat_grads, (l.rows, l.cols), (l.row_stride, l.col_stride), a_off)
+            Xt = self.ext_scratch[xt_off:xt_off + sk * l.cols].view(sk, l.cols)
+            Y = self.ext_scratch[y_off:y_off + l.rows * sk].view(l.rows, sk)
+            B = self.ext_scratch[b_off:b_off + l.cols * sk].view(l.cols, sk)
+            qo = qslot_off + P.slot_u_off(sk, sk)
+            Q = self.aux_y["arena"][qo:qo + l.rows * sk].view(l.rows, sk)
+            self.ext_views.append((A, Xt, Y, B, Q))
+        if self.gemm_impl == "auto":
+            self.gemm_impl = "tcgen05"
+        if self.gemm_impl == "tcgen05":
+            self._setup_gemm_tiles()
+
+    def _setup_gemm_tiles(self):
+        """Tile tables of the grouped tcgen05 skinny GEMMs (csrc/gemm_kernels.cu: struct GemmTile)."""
+        import struct
+        assert self.C.gemm_tile_bytes() == 72
+        gp = self.flat_grads.data_ptr()
+
+        def vec_mode(base_elems, sa_i, sa_k):
+            if sa_k == 1 and sa_i % 4 == 0 and base_elems % 4 == 0:
+                return 1
+            if sa_i == 1 and sa_k % 4 == 0 and base_elems % 4 == 0:
+                return 2
+            return 0
+
+        def tile(A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av):
+            return struct.pack("<3Q12i", A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av, 0, 0, 0)
+
+        fwd_x, fwd_b, bwd = [], [], []
+        for l, (A, Xt, Y, B, Q) in zip(self.plan.ext.layers, self.ext_views):
+            sk, m, n, rs, cs = l.sketch, l.rows, l.cols, l.row_stride, l.col_stride
+            for r0 in range(0, m, 128):      # Y[r0:r0+128] = A[r0:r0+128, :] @ X
+                base = l.off + r0 * rs
+                common = (gp + 4 * base,)
+                av = vec_mode(base, rs, cs)
+                fwd_x.append(tile(common[0], Xt.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, n, 1, sk,
+                                  min(128, m - r0), sk, n, av))
+                # power iteration: X is the (n x l) buffer B
+                fwd_b.append(tile(common[0], B.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, 1, sk, sk,
+                                  min(128, m - r0), sk, n, av))
+            for c0 in range(0, n, 128):      # B[c0:c0+128] = A[:, c0:c0+128]^T @ Q
+                base = l.off + c0 * cs
+                bwd.append(tile(gp + 4 * base, Q.data_ptr(), B.data_ptr() + 4 * c0 * sk, cs, rs, 1, sk, sk,
+                                min(128, n - c0), sk, m, vec_mode(base, cs, rs)))
+        self.n_fwd_tiles, self.n_bwd_tiles = len(fwd_x), len(bwd)
+        self.t_gemm_fwd_x = _dev_bytes(b"".join(fwd_x), self.device)
+        self.t_gemm_fwd_b = _dev_bytes(b"".join(fwd_b), self.device)
+        self.t_gemm_bwd = _dev_bytes(b"".join(bwd), self.device)
+        self.gemm_grid = torch.cuda.get_device_properties(self.device).multi_processor_count * 2
+
+    def _gemm_fwd(self, from_b: bool = False):
+        if self.gemm_impl == "tcgen05":
+            self.C.skinny_gemm(self.t_gemm_fwd_b if from_b else self.t_gemm_fwd_x, self.n_fwd_tiles, self.ctrl,
+                               self.gemm_grid)
+            return 1
+        for A, Xt, Y, B, Q in self.ext_views:
+            torch.mm(A, B if from_b else Xt.t(), out=Y)
+        return 0
+
+    def _gemm_bwd(self):
+        if self.gemm_impl == "tcgen05":
+            self.C.skinny_gemm(self.t_gemm_bwd, self.n_bwd_tiles, self.ctrl, self.gemm_grid)
+            return 1
+        for A, Xt, Y, B, Q in self.ext_views:
+            torch.mm(A.t(), Q, out=B)
+        return 0
+
+    def _aux_factorize(self, aux, rank, random_sample, signal_worker):
+        """gram -> eig_sample -> project on an auxiliary tall-skinny plan (local arena)."""
+        C, pl = self.C, aux["plan"]
+        C.gram(self.ext_scratch, aux["layers"], aux["tiles"], len(pl.enc_tiles), aux["gpart"])
+        C.eig_sample(aux["layers"], aux["ts"], aux["gpart"], aux["vsel"], aux["selcount"], None,
+                     aux["arena"].data_ptr(), 0, self.ctrl, None, rank, random_sample, self.waterfill,
+                     self.systematic, signal_worker, 256)
+        C.project_push(self.ext_scratch, aux["layers"], aux["tiles"], len(pl.enc_tiles), aux["vsel"],
+                       aux["selcount"], aux["arena"].data_ptr(), 0, self.ps_push_flags, self.ctrl, 0, False)
+        return 3
+
+    def _encode_ext(self):
+        """Randomized range finder + ATOMO sampling for the square-ish layers; factors land in the PS slot."""
+        ext = self.plan.ext
+        n = 0
+        self.ext_scratch.normal_()                       # fresh test matrices X (and scratch to overwrite)
+        n += self._gemm_fwd()                            # Y = A X            (tcgen05 skinny GEMM)
+        sk = ext.layers[0].sketch
+        n += self._aux_factorize(self.aux_y, sk, False, 0)       # Q = orth(Y)
+        for _ in range(self.power_iters):                # optional power iterations: Y = A (A^T Q)
+            n += self._gemm_bwd()
+            n += self._gemm_fwd(from_b=True)
+            n += self._aux_factorize(self.aux_y, sk, False, 0)
+        n += self._gemm_bwd()                            # B = A^T Q          (tcgen05 skinny GEMM)
+        n += self._aux_factorize(self.aux_b, self.svd_rank, self.random_sample, self.worker_index)
+        self.C.ext_finalize(self.t_ext_descs, self.t_fin_tiles, len(ext.fin_tiles), self.aux_y["arena"],
+                            self.aux_b["arena"], self.heap.region_ptr("arena", 0), self.plan.arena_floats,
+                            self.ctrl, self.worker_index)
+        return n + 1
+
     def _entry_expected(self, total: int) -> float:
         b = self.entry_budget
         return b * total if b < 1.0 else b * len(self.layout.shapes)
@@ -259,6 +388,8 @@ class FusedEngine:
         n = 0
         if self.code == "svd":
             arena0 = self.heap.region_ptr("arena", 0)
+            if pl.ext is not None:
+                n += self._encode_ext()
             if pl.enc_tiles:
                 C.gram(self.flat_grads, self.t_layers, self.t_enc_tiles, len(pl.enc_tiles), self.gpart)
                 C.eig_sample(self.t_layers, self.t_ts_layers, self.gpart, self.vsel, self.selcount, self.sigma,

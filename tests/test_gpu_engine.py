@@ -115,3 +115,78 @@ def test_two_gpu_engine_keeps_replicas_identical(code):
         assert err == 0 and same, res
         assert l1 < l0, res
     print("heap mode:", res[0][5], "multicast:", res[0][6])
+
+
+def _lowrank_plus_noise(m, n, k, dev, gen, noise=0.02):
+    a = torch.randn(m, k, device=dev, generator=gen) * torch.logspace(0, -1, k, device=dev)
+    b = torch.randn(k, n, device=dev, generator=gen)
+    return a @ b / (k ** 0.5) + noise * torch.randn(m, n, device=dev, generator=gen)
+
+
+@pytest.mark.parametrize("gemm_impl", ["torch", "tcgen05"])
+def test_subspace_route_matches_truncated_svd_and_ps_applies_it(gemm_impl):
+    """Square-ish layers (fc) go through the randomized range finder; with top-k selection the factors in
+    the PS slot must be a near-optimal rank-k approximation and ps_update must apply exactly them."""
+    from atomo_b200.models import build_model
+    from atomo_b200.ops import plan as P
+    from atomo_b200.runtime.engine import FusedEngine
+    torch.manual_seed(0)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    eng = FusedEngine(build_model("FC", 10), 0, 1, code="svd", svd_rank=3, lr=0.1, momentum=0.0, use_graph=False,
+                      random_sample=False, subspace=True, gemm_impl=gemm_impl)
+    ext = eng.plan.ext
+    assert ext is not None and len(ext.layers) == 2
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    eng.flat_grads.zero_()
+    truth = {}
+    for l in ext.layers:
+        A = _lowrank_plus_noise(l.rows, l.cols, 6, dev, gen)
+        torch.as_strided(eng.flat_grads, (l.rows, l.cols), (l.row_stride, l.col_stride), l.off).copy_(A)
+        truth[l.index] = A
+    before = eng.flat_params.clone()
+    eng._encode_push()
+    torch.cuda.synchronize()
+    arena = eng.heap.tensor("arena")
+    for l in ext.layers:
+        base = arena[l.slot_off:]
+        count = int(base[:4].view(torch.int32)[0])
+        assert count == 3
+        s = base[4:4 + count]
+        V = base[4 + l.rcap:4 + l.rcap + l.rcap * l.cols].view(l.rcap, l.cols)[:count]
+        uo = P.slot_u_off(l.rcap, l.cols)
+        U = base[uo:uo + l.rows * l.rcap].view(l.rows, l.rcap)[:, :count]
+        A = truth[l.index]
+        rec = (U * s) @ V
+        sv = torch.linalg.svdvals(A)
+        best = float(sv[3:].norm())
+        err = float((A - rec).norm())
+        assert err <= 1.25 * best + 1e-3 * float(A.norm()), (l.shape, err, best)
+        assert torch.allclose(s, sv[:3], rtol=0.05), (s, sv[:3])
+        truth[l.index] = rec
+    eng._ps_update()
+    torch.cuda.synchronize()
+    assert eng.error_code() == 0
+    for l in ext.layers:
+        p_new = torch.as_strided(eng.flat_params, (l.rows, l.cols), (l.row_stride, l.col_stride), l.off)
+        p_old = torch.as_strided(before, (l.rows, l.cols), (l.row_stride, l.col_stride), l.off)
+        assert torch.allclose(p_new, p_old - 0.1 * truth[l.index], rtol=1e-4, atol=1e-5), l.shape
+    eng.close()
+
+
+@pytest.mark.parametrize("net", ["FC", "LeNet", "VGG11"])
+def test_subspace_engine_trains(net):
+    from atomo_b200.models import build_model
+    from atomo_b200.runtime.engine import FusedEngine
+    torch.manual_seed(0)
+    torch.cuda.set_device(0)
+    eng = FusedEngine(build_model(net, 10), 0, 1, code="svd", svd_rank=3, lr=0.02, momentum=0.9, use_graph=True,
+                      subspace=True)
+    x, y = _batch(net, 64)
+    eng.prepare(x, y, warmup=2)
+    first = float(eng.train_step(x, y)[0])
+    for _ in range(40):
+        stats = eng.train_step(x, y)
+    torch.cuda.synchronize()
+    assert eng.error_code() == 0 and float(stats[0]) < first
+    eng.close()

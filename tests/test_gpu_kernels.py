@@ -286,3 +286,52 @@ def test_entrywise_kernel_matches_oracle():
     C.entrywise_scatter(ip, vp, cp, 1, cap, out, total, 0, h.ctrl, 0)
     torch.cuda.synchronize()
     assert torch.allclose(out, dense)
+
+
+def test_tcgen05_skinny_gemm_matches_fp32_matmul():
+    """Grouped tf32 tcgen05 GEMM vs torch fp32 matmul for every operand layout the subspace route uses."""
+    import struct
+    C = _ext()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    ctrl = torch.frombuffer(bytearray(__import__("atomo_b200.ops.plan", fromlist=["x"]).pack_ctrl()), dtype=torch.uint8).to(dev)
+    cases = []
+    tiles = []
+
+    def add(A_view, Bop, sb_j, sb_k, N, av_hint=None):
+        """A_view: (M_total x K) strided view; Bop element (j,k) at Bop.data_ptr + (j*sb_j + k*sb_k)*4"""
+        Mtot, K = A_view.shape
+        sa_i, sa_k = A_view.stride()
+        out = torch.zeros(Mtot, N, device=dev)
+        for r0 in range(0, Mtot, 128):
+            base_ptr = A_view.data_ptr() + 4 * r0 * sa_i
+            if sa_k == 1 and sa_i % 4 == 0 and (base_ptr // 4) % 4 == 0:
+                av = 1
+            elif sa_i == 1 and sa_k % 4 == 0 and (base_ptr // 4) % 4 == 0:
+                av = 2
+            else:
+                av = 0
+            tiles.append(struct.pack("<3Q12i", base_ptr, Bop.data_ptr(), out.data_ptr() + 4 * r0 * N, sa_i, sa_k,
+                                     sb_j, sb_k, N, min(128, Mtot - r0), N, K, av, 0, 0, 0))
+        return out
+
+    # forward: Y = A X with X^T stored (l x n); row-major A with K = 784 (not a multiple of 32), 800 rows
+    A1 = torch.randn(800, 784, device=dev)
+    Xt1 = torch.randn(16, 784, device=dev)
+    cases.append((add(A1, Xt1, 784, 1, 16), A1 @ Xt1.t()))
+    # backward: B = A^T Q (operand rows are A's columns: stride-1 along i), Q is m x l row-major
+    Q1 = torch.randn(800, 16, device=dev)
+    cases.append((add(A1.t(), Q1, 1, 16, 16), A1.t() @ Q1))
+    # transposed-orientation layer (tall view of a wide matrix), N = 32, odd sizes -> scalar gather path
+    W = torch.randn(301, 517, device=dev)
+    X2 = torch.randn(32, 301, device=dev)
+    cases.append((add(W.t(), X2, 301, 1, 32), W.t() @ X2.t()))
+    Q2 = torch.randn(517, 32, device=dev)
+    cases.append((add(W, Q2, 1, 32, 32), W @ Q2))
+    t = torch.frombuffer(bytearray(b"".join(tiles)), dtype=torch.uint8).to(dev)
+    C.skinny_gemm(t, len(tiles), ctrl, 64)
+    torch.cuda.synchronize()
+    assert int(ctrl.view(torch.int32)[1]) == 0, "tcgen05 pipeline timed out"
+    for got, ref in cases:
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 3e-3, err  # tf32 inputs (10-bit mantissa), fp32 accumulate
