@@ -44,6 +44,7 @@ DRV_FN(cuMulticastCreate);
 DRV_FN(cuMulticastAddDevice);
 DRV_FN(cuMulticastBindMem);
 DRV_FN(cuMulticastGetGranularity);
+DRV_FN(cuMulticastUnbind);
 DRV_FN(cuDeviceGetAttribute);
 DRV_FN(cuGetErrorString);
 
@@ -68,6 +69,7 @@ static bool load_driver() {
   LOAD(cuMemUnmap); LOAD(cuMemSetAccess); LOAD(cuMemGetAllocationGranularity);
   LOAD(cuMemExportToShareableHandle); LOAD(cuMemImportFromShareableHandle); LOAD(cuMulticastCreate);
   LOAD(cuMulticastAddDevice); LOAD(cuMulticastBindMem); LOAD(cuMulticastGetGranularity);
+  LOAD(cuMulticastUnbind);
   LOAD(cuDeviceGetAttribute); LOAD(cuGetErrorString);
 #undef LOAD
   state = 1;
@@ -358,7 +360,11 @@ void atomo_heap_destroy(void* hp) {
   if (!h) return;
   cudaDeviceSynchronize();
   if (h->mode == "vmm") {
-    if (h->mc_ptr) { p_cuMemUnmap((CUdeviceptr)h->mc_ptr, h->bytes); p_cuMemAddressFree((CUdeviceptr)h->mc_ptr, h->bytes); }
+    if (h->mc_ptr) {
+      p_cuMemUnmap((CUdeviceptr)h->mc_ptr, h->bytes);
+      p_cuMemAddressFree((CUdeviceptr)h->mc_ptr, h->bytes);
+      p_cuMulticastUnbind(h->mc_handle, h->device, 0, h->bytes);  // release the switch resources of this binding
+    }
     for (int p = 0; p < h->world; ++p) {
       if (h->ptrs[p]) { p_cuMemUnmap((CUdeviceptr)h->ptrs[p], h->bytes); p_cuMemAddressFree((CUdeviceptr)h->ptrs[p], h->bytes); }
       if (p != h->rank && h->peer_handles[p]) p_cuMemRelease(h->peer_handles[p]);

@@ -54,7 +54,7 @@ class FusedEngine:
                  dtype: str = "fp32", channels_last: bool = False, use_graph: bool = True, group=None,
                  multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
                  criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None,
-                 subspace: bool = True, power_iters: int = 0, gemm_impl: str = "auto"):
+                 subspace="auto", power_iters: int = 0, gemm_impl: str = "auto"):
         self.C = load_ext()
         self.rank, self.world, self.group = rank, world, group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -88,7 +88,14 @@ class FusedEngine:
         shapes = self.layout.shapes
         plan_code = self.code if self.code == "svd" else "sgd"
         self.plan = P.build_plan(shapes, plan_code, self.svd_rank, self.systematic, offsets=self.layout.offsets,
-                                 subspace=subspace)
+                                 subspace=bool(subspace))
+        if subspace == "auto" and self.plan.ext is not None:
+            # the range-finder pipeline is ~10 small dependent launches: only worth it when the square-ish
+            # layers hold a real share of the model (ResNet-50 1x1 convs, fc-heavy nets), not ResNet-18's 1.5%
+            ext_elems = sum(l.numel for l in self.plan.ext.layers)
+            if ext_elems < 0.05 * self.layout.total:
+                self.plan = P.build_plan(shapes, plan_code, self.svd_rank, self.systematic,
+                                         offsets=self.layout.offsets, subspace=False)
         self.power_iters = int(power_iters)
         self.gemm_impl = gemm_impl
         assert self.plan.total_elems == self.layout.total

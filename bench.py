@@ -30,6 +30,12 @@ sys.path.insert(0, ROOT)
 METRIC = "ResNet-18 CIFAR-10 images/sec (whole box, device-timed, max over ranks)"
 
 
+def metric_name(args):
+    if args.network == "ResNet18" and args.dataset == "Cifar10":
+        return METRIC
+    return "%s %s-shaped images/sec (whole box, device-timed, max over ranks)" % (args.network, args.dataset)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -46,6 +52,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
                     help="activations are NHWC by default (2.3x faster convs/BN on B200)")
+    ap.add_argument("--dataset", type=str, default="Cifar10", choices=["Cifar10", "ImageNet", "MNIST"])
+    ap.add_argument("--quantization-level", type=int, default=4)
+    ap.add_argument("--entry-budget", type=float, default=0.05)
+    ap.add_argument("--subspace", type=str, default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--momentum", type=float, default=0.9)
     ap.add_argument("--lr", type=float, default=0.01)
     return ap.parse_args()
@@ -135,12 +145,14 @@ def main():
 
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = build_model(args.network, 10, "Cifar10")
+    ncls = 1000 if args.dataset == "ImageNet" else 10
+    model = build_model(args.network, ncls, args.dataset)
     eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
                       ps_mode=args.ps_mode, sampling=args.sampling, dtype=args.dtype, channels_last=args.channels_last,
-                      use_graph=not args.no_graph, seed=1, timeout_s=60.0)
-    shape = input_shape(args.network, "Cifar10")
-    ds = SyntheticImageDataset(shape, 10, 50000, seed=rank)
+                      use_graph=not args.no_graph, seed=1, timeout_s=60.0, subspace={"auto": "auto", "on": True, "off": False}[args.subspace],
+                      quantization_level=args.quantization_level, entry_budget=args.entry_budget)
+    shape = input_shape(args.network, args.dataset)
+    ds = SyntheticImageDataset(shape, ncls, 50000, seed=rank)
     nbatches = 8
     xs, ys = ds.materialize(args.batch_size * nbatches)
     host_x = [xs[i * args.batch_size:(i + 1) * args.batch_size].contiguous().pin_memory() for i in range(nbatches)]
@@ -213,13 +225,14 @@ def main():
     if rank == 0:
         par = ("ps+%dworkers(colocated)" % nworkers) if args.ps_mode == "colocated" else ("ps+%dworkers" % nworkers)
         out = {
-            "metric": METRIC, "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "impl": "atomo_b200",
             "config": {"model": args.network, "global_batch": imgs_per_step, "per_worker_batch": args.batch_size,
                        "seq_len": None, "image": list(shape), "parallelism": par, "code": args.code,
-                       "svd_rank": args.svd_rank, "sampling": args.sampling, "cuda_graph": not args.no_graph,
+                       "svd_rank": args.svd_rank, "sampling": args.sampling, "dataset_shape": args.dataset,
+                       "subspace_route_layers": len(eng.plan.ext.layers) if eng.plan.ext else 0, "cuda_graph": not args.no_graph,
                        "heap": eng.heap.mode, "nvls_multicast": eng.heap.has_multicast,
                        "l2": "no explicit flush: per-step working set %.0f MB > 126 MB L2" % work_mb,
                        "optimizer": "momentum-SGD fused in PS kernel", "final_loss": round(losses[-1], 4),
