@@ -69,9 +69,16 @@ static bool load_driver() {
   LOAD(cuMemUnmap); LOAD(cuMemSetAccess); LOAD(cuMemGetAllocationGranularity);
   LOAD(cuMemExportToShareableHandle); LOAD(cuMemImportFromShareableHandle); LOAD(cuMulticastCreate);
   LOAD(cuMulticastAddDevice); LOAD(cuMulticastBindMem); LOAD(cuMulticastGetGranularity);
-  LOAD(cuMulticastUnbind);
   LOAD(cuDeviceGetAttribute); LOAD(cuGetErrorString);
 #undef LOAD
+  {  // optional (only used at teardown): never let its absence disable the VMM/NVLS path
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMulticastUnbind", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn)
+      p_cuMulticastUnbind = reinterpret_cast<decltype(p_cuMulticastUnbind)>(fn);
+    else
+      cudaGetLastError();
+  }
   state = 1;
   return true;
 }
@@ -363,7 +370,7 @@ void atomo_heap_destroy(void* hp) {
     if (h->mc_ptr) {
       p_cuMemUnmap((CUdeviceptr)h->mc_ptr, h->bytes);
       p_cuMemAddressFree((CUdeviceptr)h->mc_ptr, h->bytes);
-      p_cuMulticastUnbind(h->mc_handle, h->device, 0, h->bytes);  // release the switch resources of this binding
+      if (p_cuMulticastUnbind) p_cuMulticastUnbind(h->mc_handle, h->device, 0, h->bytes);  // release the switch binding
     }
     for (int p = 0; p < h->world; ++p) {
       if (h->ptrs[p]) { p_cuMemUnmap((CUdeviceptr)h->ptrs[p], h->bytes); p_cuMemAddressFree((CUdeviceptr)h->ptrs[p], h->bytes); }
