@@ -53,6 +53,14 @@ void atomo_launch_advance_step(void* ctrl, cudaStream_t stream);
 void atomo_launch_param_bcast(const float* src, float* const* params_peer, float* params_mc, int nranks,
                               int self_rank, long long numel, cudaStream_t stream);
 void atomo_launch_set_flags(int* const* flag_peer, int nranks, int value, cudaStream_t stream);
+// bn_kernels.cu
+void atomo_launch_bn_forward(const void* x, const void* res, void* y, long long R, int C, float* acc,
+                             const float* gamma, const float* beta, float* save_mean, float* save_invstd,
+                             float* running_mean, float* running_var, float eps, float momentum, int relu,
+                             int zero_acc, cudaStream_t stream);
+void atomo_launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, void* dres, long long R, int C,
+                              const float* mean, const float* invstd, const float* gamma, float* acc, float* dgamma,
+                              float* dbeta, int relu, int zero_acc, cudaStream_t stream);
 // gemm_kernels.cu
 int atomo_gemm_tile_bytes();
 int atomo_gemm_smem_bytes();
@@ -155,6 +163,44 @@ void project_push(const torch::Tensor& grad, const torch::Tensor& layers, const 
 void signal_push(uint64_t push_flag_peer, const torch::Tensor& ctrl, int worker_index) {
   c10::cuda::CUDAGuard guard(ctrl.device());
   atomo_launch_signal_push(P<int>(push_flag_peer), ctrl.data_ptr(), worker_index, cur_stream());
+}
+
+void check_nhwc_bf16(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name, " must be a CUDA bf16 tensor");
+  TORCH_CHECK(t.dim() == 4 && t.is_contiguous(at::MemoryFormat::ChannelsLast), name, " must be channels_last");
+  TORCH_CHECK(t.size(1) % 8 == 0 && t.size(1) <= 2048, name, ": C must be a multiple of 8 (<= 2048)");
+}
+
+void bn_forward(const torch::Tensor& x, c10::optional<torch::Tensor> res, torch::Tensor y, torch::Tensor acc,
+                const torch::Tensor& gamma, const torch::Tensor& beta, torch::Tensor save_mean,
+                torch::Tensor save_invstd, c10::optional<torch::Tensor> running_mean,
+                c10::optional<torch::Tensor> running_var, double eps, double momentum, bool relu, bool zero_acc) {
+  check_nhwc_bf16(x, "x");
+  check_nhwc_bf16(y, "y");
+  if (res.has_value()) check_nhwc_bf16(*res, "residual");
+  c10::cuda::CUDAGuard guard(x.device());
+  const long long R = x.numel() / x.size(1);
+  atomo_launch_bn_forward(x.data_ptr(), res.has_value() ? res->data_ptr() : nullptr, y.data_ptr(), R, (int)x.size(1),
+                          acc.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                          save_mean.data_ptr<float>(), save_invstd.data_ptr<float>(),
+                          running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr,
+                          running_var.has_value() ? running_var->data_ptr<float>() : nullptr, (float)eps,
+                          (float)momentum, relu ? 1 : 0, zero_acc ? 1 : 0, cur_stream());
+}
+
+void bn_backward(const torch::Tensor& dy, const torch::Tensor& x, const torch::Tensor& y, torch::Tensor dx,
+                 c10::optional<torch::Tensor> dres, const torch::Tensor& mean, const torch::Tensor& invstd,
+                 const torch::Tensor& gamma, torch::Tensor acc, torch::Tensor dgamma, torch::Tensor dbeta, bool relu,
+                 bool zero_acc) {
+  check_nhwc_bf16(dy, "dy");
+  check_nhwc_bf16(x, "x");
+  check_nhwc_bf16(dx, "dx");
+  c10::cuda::CUDAGuard guard(x.device());
+  const long long R = x.numel() / x.size(1);
+  atomo_launch_bn_backward(dy.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(),
+                           dres.has_value() ? dres->data_ptr() : nullptr, R, (int)x.size(1), mean.data_ptr<float>(),
+                           invstd.data_ptr<float>(), gamma.data_ptr<float>(), acc.data_ptr<float>(),
+                           dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), relu ? 1 : 0, zero_acc ? 1 : 0, cur_stream());
 }
 
 void skinny_gemm(const torch::Tensor& tiles, int ntiles, torch::Tensor ctrl, int grid) {
@@ -288,6 +334,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("signal_push", &signal_push);
   m.def("ext_finalize", &ext_finalize);
   m.def("skinny_gemm", &skinny_gemm);
+  m.def("bn_forward", &bn_forward);
+  m.def("bn_backward", &bn_backward);
   m.def("gemm_tile_bytes", &atomo_gemm_tile_bytes);
   m.def("gemm_smem_bytes", &atomo_gemm_smem_bytes);
   m.def("ext_desc_bytes", &atomo_ext_desc_bytes);

@@ -10,6 +10,8 @@ reference so the per-tensor coder sees the same 62 tensors.
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ..ops.fused_bn import BNAct
+
 
 class BasicBlock(nn.Module):
     expansion = 1
@@ -17,21 +19,20 @@ class BasicBlock(nn.Module):
     def __init__(self, in_planes, planes, stride=1):
         super().__init__()
         self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BNAct(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BNAct(planes)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(
                 nn.Conv2d(in_planes, self.expansion * planes, 1, stride, bias=False),
-                nn.BatchNorm2d(self.expansion * planes),
+                BNAct(self.expansion * planes),
             )
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        out = out + self.shortcut(x)
-        return F.relu(out)
+        out = self.bn1(self.conv1(x), relu=True)
+        # bn2 + residual add + ReLU in one (optionally fused) op
+        return self.bn2(self.conv2(out), residual=self.shortcut(x), relu=True)
 
 
 class Bottleneck(nn.Module):
@@ -40,24 +41,22 @@ class Bottleneck(nn.Module):
     def __init__(self, in_planes, planes, stride=1):
         super().__init__()
         self.conv1 = nn.Conv2d(in_planes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BNAct(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BNAct(planes)
         self.conv3 = nn.Conv2d(planes, self.expansion * planes, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(self.expansion * planes)
+        self.bn3 = BNAct(self.expansion * planes)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(
                 nn.Conv2d(in_planes, self.expansion * planes, 1, stride, bias=False),
-                nn.BatchNorm2d(self.expansion * planes),
+                BNAct(self.expansion * planes),
             )
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        out = out + self.shortcut(x)
-        return F.relu(out)
+        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn2(self.conv2(out), relu=True)
+        return self.bn3(self.conv3(out), residual=self.shortcut(x), relu=True)
 
 
 class ResNet(nn.Module):
@@ -69,7 +68,7 @@ class ResNet(nn.Module):
             self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         else:
             self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = BNAct(64)
         self.layer1 = self._make_layer(block, 64, num_blocks[0], 1)
         self.layer2 = self._make_layer(block, 128, num_blocks[1], 2)
         self.layer3 = self._make_layer(block, 256, num_blocks[2], 2)
@@ -84,7 +83,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn1(self.conv1(x), relu=True)
         if self.imagenet_stem:
             out = F.max_pool2d(out, 3, 2, 1)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))

@@ -54,7 +54,7 @@ class FusedEngine:
                  dtype: str = "fp32", channels_last: bool = False, use_graph: bool = True, group=None,
                  multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
                  criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None,
-                 subspace="auto", power_iters: int = 0, gemm_impl: str = "auto"):
+                 subspace="auto", power_iters: int = 0, gemm_impl: str = "auto", fused_bn="auto"):
         self.C = load_ext()
         self.rank, self.world, self.group = rank, world, group
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -134,6 +134,13 @@ class FusedEngine:
         self.signals = h.tensor("signals", torch.int32)
         bind_parameters(self.model, self.flat_params, self.layout)
         self.grad_views = bind_gradients(self.model, self.flat_grads, self.layout)
+        if fused_bn == "auto":
+            fused_bn = self.autocast and channels_last
+        if fused_bn:
+            from ..ops.fused_bn import enable_fused_bn
+            self.fused_bn_layers, self.bn_arena = enable_fused_bn(self.model, True, arena_device=self.device)
+        else:
+            self.fused_bn_layers, self.bn_arena = 0, None
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)  # activations only; weights stay flat views
             bind_parameters(self.model, self.flat_params, self.layout)
@@ -468,7 +475,10 @@ class FusedEngine:
         C.wait_params(self.local_param_flag, self.ctrl, self.timeout_ticks, self.tstats.data_ptr()); n += 1
         if self.is_worker:
             self.flat_grads.zero_()
+            if self.bn_arena is not None:
+                self.bn_arena.zero_()          # per-channel accumulators of every fused BN layer
             self._forward_backward()
+            n += 4 * self.fused_bn_layers      # stats + apply, backward reduce + apply (csrc/bn_kernels.cu)
             n += self._encode_push()
         if self.is_ps:
             n += self._ps_update()

@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--quantization-level", type=int, default=4)
     ap.add_argument("--entry-budget", type=float, default=0.05)
     ap.add_argument("--subspace", type=str, default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--fused-bn", type=str, default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--momentum", type=float, default=0.9)
     ap.add_argument("--lr", type=float, default=0.01)
     return ap.parse_args()
@@ -150,6 +151,7 @@ def main():
     eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
                       ps_mode=args.ps_mode, sampling=args.sampling, dtype=args.dtype, channels_last=args.channels_last,
                       use_graph=not args.no_graph, seed=1, timeout_s=60.0, subspace={"auto": "auto", "on": True, "off": False}[args.subspace],
+                      fused_bn={"auto": "auto", "on": True, "off": False}[args.fused_bn],
                       quantization_level=args.quantization_level, entry_budget=args.entry_budget)
     shape = input_shape(args.network, args.dataset)
     ds = SyntheticImageDataset(shape, ncls, 50000, seed=rank)
@@ -232,7 +234,8 @@ def main():
             "config": {"model": args.network, "global_batch": imgs_per_step, "per_worker_batch": args.batch_size,
                        "seq_len": None, "image": list(shape), "parallelism": par, "code": args.code,
                        "svd_rank": args.svd_rank, "sampling": args.sampling, "dataset_shape": args.dataset,
-                       "subspace_route_layers": len(eng.plan.ext.layers) if eng.plan.ext else 0, "cuda_graph": not args.no_graph,
+                       "subspace_route_layers": len(eng.plan.ext.layers) if eng.plan.ext else 0,
+                       "fused_bn_layers": eng.fused_bn_layers, "cuda_graph": not args.no_graph,
                        "heap": eng.heap.mode, "nvls_multicast": eng.heap.has_multicast,
                        "l2": "no explicit flush: per-step working set %.0f MB > 126 MB L2" % work_mb,
                        "optimizer": "momentum-SGD fused in PS kernel", "final_loss": round(losses[-1], 4),

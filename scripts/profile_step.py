@@ -50,6 +50,8 @@ def main():
 
     def fb():
         eng.flat_grads.zero_()
+        if eng.bn_arena is not None:
+            eng.bn_arena.zero_()
         eng._forward_backward()
     lines.append("eager fwd+bwd        : %.3f ms" % timed(fb))
     g = torch.cuda.CUDAGraph()
@@ -77,6 +79,8 @@ def main():
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             for _ in range(3):
                 eng.flat_grads.zero_()
+                if eng.bn_arena is not None:
+                    eng.bn_arena.zero_()
                 eng._forward_backward()
                 eng._encode_push()
                 eng._ps_update()

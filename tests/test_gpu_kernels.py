@@ -335,3 +335,43 @@ def test_tcgen05_skinny_gemm_matches_fp32_matmul():
     for got, ref in cases:
         err = float((got - ref).abs().max() / ref.abs().max())
         assert err < 3e-3, err  # tf32 inputs (10-bit mantissa), fp32 accumulate
+
+
+@pytest.mark.parametrize("C,hw,with_res,relu", [(64, 32, False, True), (128, 16, True, True), (512, 4, True, True),
+                                                (256, 8, False, False), (96, 5, True, False)])
+def test_fused_bn_matches_stock_ops(C, hw, with_res, relu):
+    """Fused BN(+residual)(+ReLU) NHWC bf16 kernels vs nn.BatchNorm2d + add + relu (fp32 reference)."""
+    import copy
+    from atomo_b200.ops.fused_bn import BNAct
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(C + hw)
+    bn = BNAct(C).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    ref = copy.deepcopy(bn)
+    bn.fused = True
+    x32 = torch.randn(16, C, hw, hw, device=dev) * 2 + 0.3
+    r32 = torch.randn(16, C, hw, hw, device=dev)
+    x = x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = r32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
+    xr = x.detach().float().requires_grad_(True)          # fp32 reference on the same (bf16-rounded) values
+    rr = r.detach().float().requires_grad_(True) if with_res else None
+    y = bn(x, residual=r, relu=relu)
+    yr = ref(xr, residual=rr, relu=relu)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(y.float(), yr, rtol=2e-2, atol=2e-2)
+    assert torch.allclose(bn.running_mean, ref.running_mean, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(bn.running_var, ref.running_var, rtol=1e-2, atol=1e-3)
+    g32 = torch.randn_like(yr)
+    y.backward(g32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    yr.backward(g32.to(torch.bfloat16).float())
+    scale = float(xr.grad.abs().max())
+    # a ReLU mask can flip where |y| ~ 0 (bf16 vs fp32 rounding): allow a vanishing fraction of outliers
+    bad = ((x.grad.float() - xr.grad).abs() > 3e-2 * scale + 1e-3).float().mean()
+    assert float(bad) < 1e-4, float(bad)
+    assert torch.allclose(bn.weight.grad, ref.weight.grad, rtol=3e-2, atol=3e-2 * float(ref.weight.grad.abs().max()))
+    assert torch.allclose(bn.bias.grad, ref.bias.grad, rtol=3e-2, atol=3e-2 * float(ref.bias.grad.abs().max()))
+    if with_res:
+        bad = ((r.grad.float() - rr.grad).abs() > 2e-2 * float(rr.grad.abs().max()) + 1e-3).float().mean()
+        assert float(bad) < 1e-4, float(bad)
