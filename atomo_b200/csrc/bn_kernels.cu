@@ -212,6 +212,14 @@ static int bn_grid(long long work_items, int per_block) {
   if (g < 1) g = 1;
   return (int)g;
 }
+// reduction kernels: rows handled per thread, chosen so that even the small late layers (R = 2048)
+// launch ~2 waves of CTAs instead of 32 latency-bound ones
+static int bn_reduce_grid(long long R, int RL) {
+  long long rpt = R / ((long long)RL * 148 * 4);
+  if (rpt < 1) rpt = 1;
+  if (rpt > 16) rpt = 16;
+  return bn_grid(R, RL * (int)rpt);
+}
 
 void atomo_launch_bn_forward(const void* x, const void* res, void* y, long long R, int C, float* acc,
                              const float* gamma, const float* beta, float* save_mean, float* save_invstd,
@@ -219,9 +227,9 @@ void atomo_launch_bn_forward(const void* x, const void* res, void* y, long long 
                              int zero_acc, cudaStream_t stream) {
   const int CG = C / 8, RL = BN_THREADS / CG;
   if (zero_acc) cudaMemsetAsync(acc, 0, sizeof(float) * 2 * C, stream);
-  const int g1 = bn_grid(R, RL * 16);
+  const int g1 = bn_reduce_grid(R, RL);
   bn_stats_kernel<<<g1, BN_THREADS, 2 * RL * C * sizeof(float), stream>>>((const uint4*)x, R, C, acc);
-  const int g2 = bn_grid(R * CG, BN_THREADS * 4);
+  const int g2 = bn_grid(R * CG, BN_THREADS * 2);
   bn_apply_kernel<<<g2, BN_THREADS, 2 * C * sizeof(float), stream>>>((const uint4*)x, (const uint4*)res, (uint4*)y, R,
                                                                      C, acc, gamma, beta, save_mean, save_invstd,
                                                                      running_mean, running_var, eps, momentum, relu);
@@ -232,11 +240,11 @@ void atomo_launch_bn_backward(const void* dy, const void* x, const void* y, void
                               float* dbeta, int relu, int zero_acc, cudaStream_t stream) {
   const int CG = C / 8, RL = BN_THREADS / CG;
   if (zero_acc) cudaMemsetAsync(acc, 0, sizeof(float) * 2 * C, stream);
-  const int g1 = bn_grid(R, RL * 16);
+  const int g1 = bn_reduce_grid(R, RL);
   bn_bwd_reduce_kernel<<<g1, BN_THREADS, 2 * RL * C * sizeof(float), stream>>>((const uint4*)dy, (const uint4*)x,
                                                                                (const uint4*)y, R, C, mean, invstd,
                                                                                acc, relu);
-  const int g2 = bn_grid(R * CG, BN_THREADS * 4);
+  const int g2 = bn_grid(R * CG, BN_THREADS * 2);
   bn_bwd_apply_kernel<<<g2, BN_THREADS, 5 * C * sizeof(float), stream>>>((const uint4*)dy, (const uint4*)x,
                                                                          (const uint4*)y, (uint4*)dx, (uint4*)dres, R,
                                                                          C, mean, invstd, gamma, acc, dgamma, dbeta,

@@ -23,7 +23,9 @@ struct GemmTile {
   int sa_i, sa_k, sb_j, sb_k;
   int ldc, M, N, K;  // M <= 128 valid rows in this tile, N in {16, 32}
   int a_vec;         // 1: float4 along k legal, 2: float4 along i legal, 0: scalar gather
-  int pad0, pad1, pad2;
+  int k_begin;       // split-K: this tile reduces k in [k_begin, k_begin + k_len)   (k_len == 0 -> whole K)
+  int k_len;
+  int atomic;        // 1: accumulate into C with atomicAdd (split-K partial sums; C pre-zeroed)
 };
 
 constexpr int GEMM_THREADS = 128;
@@ -119,9 +121,100 @@ skinny_gemm_tf32_kernel(const GemmTile* __restrict__ tiles, int ntiles, Ctrl* ct
   int fail = 0;     // made CTA-uniform at every barrier (__syncthreads_or): a timed-out wait never deadlocks the CTA
   for (int ti = blockIdx.x; ti < ntiles && !fail; ti += gridDim.x) {
     const GemmTile T = tiles[ti];
-    const int nchunks = (T.K + GEMM_KC - 1) / GEMM_KC;
+    const int kb = T.k_begin;
+    const int kend = T.k_len > 0 ? min(T.K, kb + T.k_len) : T.K;
+    const int nchunks = (kend - kb + GEMM_KC - 1) / GEMM_KC;
     const uint32_t idesc = make_idesc_tf32(128, T.N);
 
+    // register staging: the global loads of chunk kc+1 are issued before the barrier / MMA of chunk kc,
+    // so DRAM latency overlaps the tensor-core work and the shared-memory hand-off
+    float ra[32];
+    float rb[8];
+    auto load_regs = [&](int k0) {
+      if (T.a_vec == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          const int i = e >> 3, k = k0 + 4 * (e & 7);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < T.M && k < kend) {
+            const float* src = T.A + (long long)i * T.sa_i + k;
+            if (k + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(src));
+            else { v.x = __ldg(src); if (k + 1 < kend) v.y = __ldg(src + 1); if (k + 2 < kend) v.z = __ldg(src + 2); }
+          }
+          ra[4 * q] = v.x; ra[4 * q + 1] = v.y; ra[4 * q + 2] = v.z; ra[4 * q + 3] = v.w;
+        }
+      } else if (T.a_vec == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          const int kk = e >> 5, i = 4 * (e & 31), k = k0 + kk;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < kend && i < T.M) {
+            const float* src = T.A + i + (long long)k * T.sa_k;
+            if (i + 3 < T.M) v = __ldg(reinterpret_cast<const float4*>(src));
+            else { v.x = __ldg(src); if (i + 1 < T.M) v.y = __ldg(src + 1); if (i + 2 < T.M) v.z = __ldg(src + 2); }
+          }
+          ra[4 * q] = v.x; ra[4 * q + 1] = v.y; ra[4 * q + 2] = v.z; ra[4 * q + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          const int i = e >> 5, k = k0 + (e & 31);
+          ra[q] = (i < T.M && k < kend) ? __ldg(T.A + (long long)i * T.sa_i + (long long)k * T.sa_k) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = tid + q * GEMM_THREADS;
+        float v = 0.f;
+        if (e < T.N * GEMM_KC) {
+          int j, kk;
+          if (T.sb_k == 1) { j = e >> 5; kk = e & 31; }
+          else { kk = e / T.N; j = e - kk * T.N; }
+          const int k = k0 + kk;
+          if (k < kend) v = __ldg(T.B + (long long)j * T.sb_j + (long long)k * T.sb_k);
+        }
+        rb[q] = v;
+      }
+    };
+    auto store_regs = [&](int s) {
+      if (T.a_vec == 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          *reinterpret_cast<float4*>(sA[s] + core_off(e >> 3, 4 * (e & 7))) =
+              make_float4(ra[4 * q], ra[4 * q + 1], ra[4 * q + 2], ra[4 * q + 3]);
+        }
+      } else if (T.a_vec == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          const int kk = e >> 5, i = 4 * (e & 31);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<float*>(sA[s] + core_off(i + j, kk)) = ra[4 * q + j];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int e = tid + q * GEMM_THREADS;
+          *reinterpret_cast<float*>(sA[s] + core_off(e >> 5, e & 31)) = ra[q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = tid + q * GEMM_THREADS;
+        if (e < T.N * GEMM_KC) {
+          int j, kk;
+          if (T.sb_k == 1) { j = e >> 5; kk = e & 31; }
+          else { kk = e / T.N; j = e - kk * T.N; }
+          *reinterpret_cast<float*>(sB[s] + core_off(j, kk)) = rb[q];
+        }
+      }
+    };
+
+    load_regs(kb);
     for (int kc = 0; kc < nchunks && !fail; ++kc, ++it) {
       const int s = it & 1;
       const uint32_t uses = it >> 1;  // previous uses of this stage
@@ -129,51 +222,8 @@ skinny_gemm_tf32_kernel(const GemmTile* __restrict__ tiles, int ntiles, Ctrl* ct
         // the MMAs that read this stage last time must have drained it
         if (!mbar_wait(&bar_free[s], (uses - 1) & 1)) fail = 1;
       }
-      const int k0 = kc * GEMM_KC;
-      // ---- stage the A chunk: 128 rows x 32 k (zero-filled outside the matrix) -----------------------
-      if (T.a_vec == 1) {
-        for (int e = tid; e < 128 * (GEMM_KC / 4); e += GEMM_THREADS) {
-          const int i = e >> 3, k4 = e & 7, k = k0 + 4 * k4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < T.M && k < T.K) {
-            const float* src = T.A + (long long)i * T.sa_i + k;
-            if (k + 3 < T.K) v = __ldg(reinterpret_cast<const float4*>(src));
-            else { v.x = __ldg(src); if (k + 1 < T.K) v.y = __ldg(src + 1); if (k + 2 < T.K) v.z = __ldg(src + 2); }
-          }
-          *reinterpret_cast<float4*>(sA[s] + core_off(i, 4 * k4)) = v;
-        }
-      } else if (T.a_vec == 2) {
-        for (int e = tid; e < (128 / 4) * GEMM_KC; e += GEMM_THREADS) {
-          const int kk = e >> 5, i4 = e & 31, i = 4 * i4, k = k0 + kk;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < T.K && i < T.M) {
-            const float* src = T.A + i + (long long)k * T.sa_k;
-            if (i + 3 < T.M) v = __ldg(reinterpret_cast<const float4*>(src));
-            else { v.x = __ldg(src); if (i + 1 < T.M) v.y = __ldg(src + 1); if (i + 2 < T.M) v.z = __ldg(src + 2); }
-          }
-          *reinterpret_cast<float*>(sA[s] + core_off(i, kk)) = v.x;
-          *reinterpret_cast<float*>(sA[s] + core_off(i + 1, kk)) = v.y;
-          *reinterpret_cast<float*>(sA[s] + core_off(i + 2, kk)) = v.z;
-          *reinterpret_cast<float*>(sA[s] + core_off(i + 3, kk)) = v.w;
-        }
-      } else {
-        for (int e = tid; e < 128 * GEMM_KC; e += GEMM_THREADS) {
-          const int i = e >> 5, kk = e & 31, k = k0 + kk;
-          float v = 0.f;
-          if (i < T.M && k < T.K) v = __ldg(T.A + (long long)i * T.sa_i + (long long)k * T.sa_k);
-          *reinterpret_cast<float*>(sA[s] + core_off(i, kk)) = v;
-        }
-      }
-      // ---- stage the skinny operand: N rows x 32 k ------------------------------------------------------
-      for (int e = tid; e < T.N * GEMM_KC; e += GEMM_THREADS) {
-        int j, kk;
-        if (T.sb_k == 1) { j = e >> 5; kk = e & 31; }        // k contiguous in memory
-        else { kk = e / T.N; j = e - kk * T.N; }              // j contiguous in memory
-        const int k = k0 + kk;
-        float v = 0.f;
-        if (k < T.K) v = __ldg(T.B + (long long)j * T.sb_j + (long long)k * T.sb_k);
-        *reinterpret_cast<float*>(sB[s] + core_off(j, kk)) = v;
-      }
+      store_regs(s);
+      if (kc + 1 < nchunks) load_regs(kb + (kc + 1) * GEMM_KC);  // in flight across the barrier and the MMAs
       // generic-proxy writes -> visible to the tensor core's async proxy
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       fail = __syncthreads_or(fail);
@@ -210,7 +260,10 @@ skinny_gemm_tf32_kernel(const GemmTile* __restrict__ tiles, int ntiles, Ctrl* ct
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int i = tid;  // TMEM lane == output row
-      if (i < T.M && !fail) {
+      if (i < T.M && !fail && T.atomic) {
+        float* dst = T.C + (long long)i * T.ldc;
+        for (int j = 0; j < T.N; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));  // split-K partial sum
+      } else if (i < T.M && !fail) {
         float* dst = T.C + (long long)i * T.ldc;
         if ((T.ldc & 3) == 0 && (((uintptr_t)dst) & 15) == 0) {
           for (int j = 0; j < T.N; j += 4)

@@ -239,6 +239,9 @@ class ExtPlan:
     scratch_floats: int
     local_arena_floats: int
     fin_tiles: List[Tuple[int, int, int, int]]
+    xt_range: Tuple[int, int] = (0, 0)
+    y_range: Tuple[int, int] = (0, 0)
+    b_range: Tuple[int, int] = (0, 0)
 
     def descs_bytes(self) -> bytes:
         return b"".join(struct.pack(EXT_FMT, *d) for d in self.descs)
@@ -268,13 +271,18 @@ def _aux_plan(entries, rank, systematic, topk_all: bool) -> Plan:
 
 
 def build_ext_plan(ext_layers: List[Layer], rank: int, systematic: bool) -> ExtPlan:
-    scratch = 0
+    # scratch = [all X^T | all Y | all B]: each group can be (re)initialised with ONE launch
+    xt_total = sum(_round_up(l.sketch * l.cols, ALIGN_ELEMS) for l in ext_layers)
+    y_total = sum(_round_up(l.rows * l.sketch, ALIGN_ELEMS) for l in ext_layers)
+    b_total = sum(_round_up(l.cols * l.sketch, ALIGN_ELEMS) for l in ext_layers)
+    xt_cur, y_cur, b_cur = 0, xt_total, xt_total + y_total
+    scratch = xt_total + y_total + b_total
     descs, y_entries, b_entries, fin_tiles = [], [], [], []
     for l in ext_layers:
         sk = l.sketch
-        xt_off = scratch; scratch += _round_up(sk * l.cols, ALIGN_ELEMS)
-        y_off = scratch; scratch += _round_up(l.rows * sk, ALIGN_ELEMS)
-        b_off = scratch; scratch += _round_up(l.cols * sk, ALIGN_ELEMS)
+        xt_off = xt_cur; xt_cur += _round_up(sk * l.cols, ALIGN_ELEMS)
+        y_off = y_cur; y_cur += _round_up(l.rows * sk, ALIGN_ELEMS)
+        b_off = b_cur; b_cur += _round_up(l.cols * sk, ALIGN_ELEMS)
         y_entries.append((y_off, l.rows, sk, sk))        # orthonormalise: keep all l atoms
         b_entries.append((b_off, l.cols, sk, l.rcap))    # factorise + sample
         descs.append([l.off, xt_off, y_off, b_off, 0, 0, l.slot_off, 0,
@@ -285,8 +293,10 @@ def build_ext_plan(ext_layers: List[Layer], rank: int, systematic: bool) -> ExtP
     aux_b = _aux_plan(b_entries, rank, systematic, False)
     for d, ly, lb in zip(descs, aux_y.layers, aux_b.layers):
         d[4], d[5] = ly.slot_off, lb.slot_off  # Q slot / B slot inside their local arenas
-    return ExtPlan(ext_layers, [tuple(d) for d in descs], aux_y, aux_b, max(scratch, 32),
-                   aux_y.arena_floats + aux_b.arena_floats, fin_tiles)
+    ep = ExtPlan(ext_layers, [tuple(d) for d in descs], aux_y, aux_b, max(scratch, 32),
+                 aux_y.arena_floats + aux_b.arena_floats, fin_tiles)
+    ep.xt_range, ep.y_range, ep.b_range = (0, xt_total), (xt_total, xt_total + y_total), (xt_total + y_total, scratch)
+    return ep
 
 
 def dense_only_plan(shapes, offsets=None) -> Plan:

@@ -264,33 +264,56 @@ class FusedEngine:
                 return 2
             return 0
 
-        def tile(A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av):
-            return struct.pack("<3Q12i", A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av, 0, 0, 0)
+        def tile(A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av, kb=0, klen=0, atomic=0):
+            return struct.pack("<3Q12i", A_ptr, B_ptr, C_ptr, sa_i, sa_k, sb_j, sb_k, ldc, M, N, K, av, kb, klen,
+                               atomic)
 
+        def ksplits(ntiles, K):
+            """split the reduction so that a handful of output tiles still fills the 148 SMs"""
+            want = -(-296 // max(ntiles, 1))
+            return max(1, min(want, K // 128))
+
+        layers = self.plan.ext.layers
+        n_f = sum(-(-l.rows // 128) for l in layers)
+        n_b = sum(-(-l.cols // 128) for l in layers)
         fwd_x, fwd_b, bwd = [], [], []
-        for l, (A, Xt, Y, B, Q) in zip(self.plan.ext.layers, self.ext_views):
+        self.gemm_fwd_atomic = self.gemm_bwd_atomic = False
+        for l, (A, Xt, Y, B, Q) in zip(layers, self.ext_views):
             sk, m, n, rs, cs = l.sketch, l.rows, l.cols, l.row_stride, l.col_stride
+            sf, sb = ksplits(n_f, n), ksplits(n_b, m)
+            klen_f = -(-(-(-n // sf)) // 32) * 32
+            klen_b = -(-(-(-m // sb)) // 32) * 32
             for r0 in range(0, m, 128):      # Y[r0:r0+128] = A[r0:r0+128, :] @ X
                 base = l.off + r0 * rs
-                common = (gp + 4 * base,)
                 av = vec_mode(base, rs, cs)
-                fwd_x.append(tile(common[0], Xt.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, n, 1, sk,
-                                  min(128, m - r0), sk, n, av))
-                # power iteration: X is the (n x l) buffer B
-                fwd_b.append(tile(common[0], B.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, 1, sk, sk,
-                                  min(128, m - r0), sk, n, av))
+                for kb in range(0, n, klen_f):
+                    at = int(sf > 1)
+                    self.gemm_fwd_atomic |= bool(at)
+                    fwd_x.append(tile(gp + 4 * base, Xt.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, n, 1, sk,
+                                      min(128, m - r0), sk, n, av, kb, klen_f, at))
+                    # power iteration: X is the (n x l) buffer B
+                    fwd_b.append(tile(gp + 4 * base, B.data_ptr(), Y.data_ptr() + 4 * r0 * sk, rs, cs, 1, sk, sk,
+                                      min(128, m - r0), sk, n, av, kb, klen_f, at))
             for c0 in range(0, n, 128):      # B[c0:c0+128] = A[:, c0:c0+128]^T @ Q
                 base = l.off + c0 * cs
-                bwd.append(tile(gp + 4 * base, Q.data_ptr(), B.data_ptr() + 4 * c0 * sk, cs, rs, 1, sk, sk,
-                                min(128, n - c0), sk, m, vec_mode(base, cs, rs)))
+                for kb in range(0, m, klen_b):
+                    at = int(sb > 1)
+                    self.gemm_bwd_atomic |= bool(at)
+                    bwd.append(tile(gp + 4 * base, Q.data_ptr(), B.data_ptr() + 4 * c0 * sk, cs, rs, 1, sk, sk,
+                                    min(128, n - c0), sk, m, vec_mode(base, cs, rs), kb, klen_b, at))
         self.n_fwd_tiles, self.n_bwd_tiles = len(fwd_x), len(bwd)
         self.t_gemm_fwd_x = _dev_bytes(b"".join(fwd_x), self.device)
         self.t_gemm_fwd_b = _dev_bytes(b"".join(fwd_b), self.device)
         self.t_gemm_bwd = _dev_bytes(b"".join(bwd), self.device)
         self.gemm_grid = torch.cuda.get_device_properties(self.device).multi_processor_count * 2
+        ext = self.plan.ext
+        self.ext_y_all = self.ext_scratch[ext.y_range[0]:ext.y_range[1]]
+        self.ext_b_all = self.ext_scratch[ext.b_range[0]:ext.b_range[1]]
 
     def _gemm_fwd(self, from_b: bool = False):
         if self.gemm_impl == "tcgen05":
+            if self.gemm_fwd_atomic:
+                self.ext_y_all.zero_()   # split-K partial sums are accumulated with atomics
             self.C.skinny_gemm(self.t_gemm_fwd_b if from_b else self.t_gemm_fwd_x, self.n_fwd_tiles, self.ctrl,
                                self.gemm_grid)
             return 1
@@ -300,6 +323,8 @@ class FusedEngine:
 
     def _gemm_bwd(self):
         if self.gemm_impl == "tcgen05":
+            if self.gemm_bwd_atomic:
+                self.ext_b_all.zero_()
             self.C.skinny_gemm(self.t_gemm_bwd, self.n_bwd_tiles, self.ctrl, self.gemm_grid)
             return 1
         for A, Xt, Y, B, Q in self.ext_views:
@@ -321,7 +346,8 @@ class FusedEngine:
         """Randomized range finder + ATOMO sampling for the square-ish layers; factors land in the PS slot."""
         ext = self.plan.ext
         n = 0
-        self.ext_scratch.normal_()                       # fresh test matrices X (and scratch to overwrite)
+        xr = ext.xt_range
+        self.ext_scratch[xr[0]:xr[1]].normal_()          # fresh Gaussian test matrices X for every layer
         n += self._gemm_fwd()                            # Y = A X            (tcgen05 skinny GEMM)
         sk = ext.layers[0].sketch
         n += self._aux_factorize(self.aux_y, sk, False, 0)       # Q = orth(Y)

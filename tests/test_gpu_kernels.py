@@ -298,7 +298,7 @@ def test_tcgen05_skinny_gemm_matches_fp32_matmul():
     cases = []
     tiles = []
 
-    def add(A_view, Bop, sb_j, sb_k, N, av_hint=None):
+    def add(A_view, Bop, sb_j, sb_k, N, splits=1):
         """A_view: (M_total x K) strided view; Bop element (j,k) at Bop.data_ptr + (j*sb_j + k*sb_k)*4"""
         Mtot, K = A_view.shape
         sa_i, sa_k = A_view.stride()
@@ -311,8 +311,10 @@ def test_tcgen05_skinny_gemm_matches_fp32_matmul():
                 av = 2
             else:
                 av = 0
-            tiles.append(struct.pack("<3Q12i", base_ptr, Bop.data_ptr(), out.data_ptr() + 4 * r0 * N, sa_i, sa_k,
-                                     sb_j, sb_k, N, min(128, Mtot - r0), N, K, av, 0, 0, 0))
+            klen = -(-(-(-K // splits)) // 32) * 32
+            for kb in range(0, K, klen):
+                tiles.append(struct.pack("<3Q12i", base_ptr, Bop.data_ptr(), out.data_ptr() + 4 * r0 * N, sa_i, sa_k,
+                                         sb_j, sb_k, N, min(128, Mtot - r0), N, K, av, kb, klen, int(splits > 1)))
         return out
 
     # forward: Y = A X with X^T stored (l x n); row-major A with K = 784 (not a multiple of 32), 800 rows
@@ -322,6 +324,8 @@ def test_tcgen05_skinny_gemm_matches_fp32_matmul():
     # backward: B = A^T Q (operand rows are A's columns: stride-1 along i), Q is m x l row-major
     Q1 = torch.randn(800, 16, device=dev)
     cases.append((add(A1.t(), Q1, 1, 16, 16), A1.t() @ Q1))
+    cases.append((add(A1.t(), Q1, 1, 16, 16, splits=5), A1.t() @ Q1))   # split-K with atomic accumulation
+    cases.append((add(A1, Xt1, 784, 1, 16, splits=3), A1 @ Xt1.t()))
     # transposed-orientation layer (tall view of a wide matrix), N = 32, odd sizes -> scalar gather path
     W = torch.randn(301, 517, device=dev)
     X2 = torch.randn(32, 301, device=dev)
