@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--entry-budget", type=float, default=0.05)
     ap.add_argument("--subspace", type=str, default="auto", choices=["auto", "on", "off"])
     ap.add_argument("--fused-bn", type=str, default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--no-cudnn-benchmark", dest="cudnn_benchmark", action="store_false", default=True)
     ap.add_argument("--momentum", type=float, default=0.9)
     ap.add_argument("--lr", type=float, default=0.01)
     return ap.parse_args()
@@ -145,7 +146,7 @@ def main():
     from atomo_b200.runtime.engine import FusedEngine
 
     torch.manual_seed(0)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = args.cudnn_benchmark
     ncls = 1000 if args.dataset == "ImageNet" else 10
     model = build_model(args.network, ncls, args.dataset)
     eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
