@@ -10,12 +10,14 @@ Routing (what the reference does per tensor vs. what is sent here):
 * the factorization always works on the *tall* orientation (rows >= cols); a
   wide matrix such as fc ``(10, 512)`` is handled as its transpose through the
   ``row_stride/col_stride`` fields, no copy;
-* ``cols <= 64`` -> ``ROUTE_SVD_TS``: complete Gram/Jacobi SVD (every 3x3 /
-  5x5 conv of the model zoo: cols = 18 / 50);
+* ``cols <= 32`` (or ``<= 64`` when really tall) -> ``ROUTE_SVD_TS``: complete
+  Gram/Jacobi SVD (every 3x3 / 5x5 conv of the model zoo: cols = 18 / 50);
 * 1-D tensors (BN, biases; rank <= 2) travel dense: coding them costs more
   bytes than the tensor itself (SURVEY.md 2.4, consequence 2);
-* ``cols > 64`` -> dense in this round (``ROUTE_LOWRANK_EXT`` is reserved for
-  the subspace-iteration path).
+* square-ish layers (fc, 1x1 convs) -> ``ROUTE_LOWRANK_EXT`` when ``subspace``
+  is on: randomized range finder of width ``sketch`` on the tcgen05 skinny
+  GEMMs, then the same Gram/Jacobi machinery on auxiliary plans (``ExtPlan``);
+  otherwise dense.
 """
 from __future__ import annotations
 
