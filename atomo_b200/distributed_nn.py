@@ -36,7 +36,9 @@ def _kwargs(args, role: str) -> dict:
     if role == "master":
         kw.update({"num_aggregate": args.num_aggregate, "lr_shrinkage": args.lr_shrinkage,
                    "optimizer": args.optimizer, "weight_decay": args.weight_decay, "nesterov": args.nesterov,
-                   "resume": args.resume})
+                   "resume": args.resume, "kill_stragglers": args.straggler_kill})
+    else:
+        kw["split_backward"] = args.straggler_kill
     return kw
 
 

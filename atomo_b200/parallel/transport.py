@@ -50,7 +50,7 @@ class Transport:
     def gather(self, step: int, need: Optional[int] = None): raise NotImplementedError
     def send_kill(self, worker_rank: int) -> None: raise NotImplementedError
     def drain(self) -> int: return 0
-    def kill_requested(self) -> bool: return False
+    def kill_requested(self, step=None) -> bool: return False
     def barrier(self) -> None: raise NotImplementedError
 
 
@@ -138,7 +138,10 @@ class TorchDistTransport(Transport):
                 cursor += 1
             self._recv_count[sender] = self._recv_count.get(sender, 0) + 1
             if msg_step == step:
-                got[sender] = wire.unpack(buf)["codes"]
+                codes = wire.unpack(buf)["codes"]
+                if codes is None:      # the worker abandoned this step after a kill signal
+                    continue
+                got[sender] = codes
             else:  # stale gradient from a straggler: drop
                 self._stale_dropped += 1
         return got
@@ -155,35 +158,39 @@ class TorchDistTransport(Transport):
         self._stale_dropped += dropped
         return dropped
 
-    # -- straggler kill signal (tag 77) -------------------------------------
-    def send_kill(self, worker_rank: int, step: int = 0) -> None:
-        t = torch.tensor([step], dtype=torch.int64, device=self.device)
-        dist.send(t, dst=worker_rank, group=self.group, tag=77)
-
-    def _kill_listener(self):
-        buf = torch.zeros(1, dtype=torch.int64, device=self.device)
-        while True:
+    # -- straggler kill signal (the reference's tag 77) ------------------------
+    # The reference polls ``Iprobe(0, 77)`` between layer backwards (lenet.py:173-180).  gloo has no
+    # probe and a blocking listener thread fights the compute threads, so the signal travels through
+    # the rendezvous key-value store instead: a step-stamped key per worker, checked without blocking.
+    def _store(self):
+        if getattr(self, "_kv", None) is None:
             try:
-                dist.recv(buf, src=0, group=self.group, tag=77)
+                from torch.distributed.distributed_c10d import _get_default_store
+                self._kv = _get_default_store()
             except Exception:
-                return
-            self._kill_flag.set()
+                self._kv = False
+        return None if self._kv is False else self._kv
+
+    def send_kill(self, worker_rank: int, step: int = 0) -> None:
+        kv = self._store()
+        if kv is not None:
+            kv.set("atomo_b200/kill/%d" % worker_rank, str(step))
 
     def enable_kill_listener(self) -> None:
-        """Worker side: start a daemon thread blocking on tag 77 (the reference
-        polls ``Iprobe`` between layer backwards, lenet.py:173-180)."""
-        import threading
-        if getattr(self, "_kill_thread", None) is None:
-            self._kill_flag = threading.Event()
-            self._kill_thread = threading.Thread(target=self._kill_listener, daemon=True)
-            self._kill_thread.start()
+        self._kill_enabled = self._store() is not None
 
-    def kill_requested(self) -> bool:
-        flag = getattr(self, "_kill_flag", None)
-        if flag is not None and flag.is_set():
-            flag.clear()
-            return True
-        return False
+    def kill_requested(self, step: Optional[int] = None) -> bool:
+        if not getattr(self, "_kill_enabled", False):
+            return False
+        kv, key = self._store(), "atomo_b200/kill/%d" % self.rank
+        try:
+            if not kv.check([key]):
+                return False
+            stamped = int(kv.get(key))
+        except Exception:
+            return False
+        # signals are step-stamped: a late one for step t cannot abort step t+1
+        return step is None or stamped == step
 
     def barrier(self) -> None:
         dist.barrier(group=self.group)

@@ -54,12 +54,24 @@ class DistributedWorker(NN_Trainer):
         self._bucket_size = kwargs.get("bucket_size", 512)
         self._code = kwargs.get("code", "sgd")
         self._eval_batches = kwargs.get("eval_batches", None)
+        # layer-wise backward with gradient emission + straggler kill (the reference's *Split models,
+        # resnet_split.py:458-570): encode each layer as soon as its gradient exists, abandon the step when
+        # the PS signals (tag 77) that it already has enough gradients
+        self._split_backward = bool(kwargs.get("split_backward", False))
         self.device = torch.device("cuda", torch.cuda.current_device()) if self._enable_gpu else torch.device("cpu")
         self._coder = build_coder(kwargs, worker_side=True)
         self.last_stats = {}
 
     def build_model(self, num_classes: int = 10):
-        self.network = build_model(self.network_config, num_classes, self.dataset).to(self.device)
+        self.network = build_model(self.network_config, num_classes, self.dataset)
+        if self._split_backward:
+            from ..models.split import FC_NN_Split, LeNetSplit, ResNetSplit18, ResNetSplit34
+            split = {"LeNet": LeNetSplit, "FC": FC_NN_Split, "ResNet18": ResNetSplit18, "ResNet34": ResNetSplit34}
+            if self.network_config not in split:
+                raise ValueError("split backward is available for %s" % ", ".join(sorted(split)))
+            self.network = split[self.network_config](num_classes=num_classes)
+            self.comm.enable_kill_listener()
+        self.network = self.network.to(self.device)
         self.layout = FlatLayout.from_module(self.network)
         # the receive buffer IS the parameter storage (parity role: ModelBuffer, worker:84-95)
         self.flat_params = torch.zeros(self.layout.total, dtype=torch.float32, device=self.device)
@@ -93,12 +105,27 @@ class DistributedWorker(NN_Trainer):
                 comp_start = time.time()
                 logits = self.network(x)
                 loss = self.criterion(logits, y)
-                loss.backward()
-                comp_dur = time.time() - comp_start
-
-                encode_start = time.time()
-                msgs, msg_bytes = self._encode()
-                encode_dur = time.time() - encode_start
+                if self._split_backward:
+                    emitted = {}
+                    killed = self.network.backward_signal_kill(
+                        loss, emit=lambda i, p, g: emitted.__setitem__(i, self._coder.encode(g.detach().float())),
+                        kill_signal=lambda: self.comm.kill_requested(self.cur_step), cur_step=self.cur_step)
+                    comp_dur = time.time() - comp_start
+                    if killed:
+                        print("Worker: {}, Step: {} abandoned (PS already aggregated enough gradients)".format(
+                            self.rank, self.cur_step))
+                        self.comm.push(None, self.cur_step)
+                        continue
+                    encode_start = time.time()
+                    msgs = [emitted[i] for i in range(len(emitted))]
+                    msg_bytes = sum(Coding.wire_bytes(c) for c in msgs)
+                    encode_dur = time.time() - encode_start
+                else:
+                    loss.backward()
+                    comp_dur = time.time() - comp_start
+                    encode_start = time.time()
+                    msgs, msg_bytes = self._encode()
+                    encode_dur = time.time() - encode_start
 
                 comm_start = time.time()
                 self._send_grads(msgs)

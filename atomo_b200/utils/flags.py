@@ -59,6 +59,9 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--dtype", type=str, default="fp32", choices=["fp32", "bf16"])
     p.add_argument("--ps-mode", type=str, default="colocated", choices=["colocated", "dedicated"],
                    help="p2p backend: rank 0 hosts the PS and (colocated) also trains")
+    p.add_argument("--straggler-kill", type=bool_flag, default=False,
+                   help="with --num-aggregate < workers: layer-wise (split) backward on the workers and a tag-77 kill "
+                        "signal from the PS once enough gradients arrived (LeNet / FC / ResNet18 / ResNet34)")
     p.add_argument("--master-addr", type=str, default="127.0.0.1")
     p.add_argument("--master-port", type=int, default=29511)
     p.add_argument("--eval-batches", type=int, default=0, help="cap test batches per evaluation (0 = all)")

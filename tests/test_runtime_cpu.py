@@ -166,3 +166,29 @@ def test_data_sharding_and_loader():
         assert x.shape == (16, 3, 32, 32)
     assert ld.epochs_completed >= 1
     ld.close()
+
+
+def test_straggler_kill_split_backward(tmp_path):
+    """--num-aggregate 1 of 2 workers + --straggler-kill: workers run the layer-wise (split) backward with a
+    kill listener, the PS signals the straggler and drops whatever it still sends; training completes."""
+    out = _run_launcher(["--nproc", "3", "--network", "LeNet", "--dataset", "MNIST", "--code", "svd", "--svd-rank", "2",
+                         "--max-steps", "5", "--num-aggregate", "1", "--straggler-kill", "1", "--eval-freq", "100",
+                         "--train-dir", str(tmp_path) + "/", "--master-port", "29591"])
+    assert "Master: Step: 5" in out
+    steps = [l for l in out.splitlines() if l.startswith("Worker:")]
+    assert len(steps) >= 5  # every step is completed by at least one worker (others may have been abandoned)
+
+
+def test_kill_signal_is_step_stamped():
+    from atomo_b200.parallel.transport import TorchDistTransport
+
+    class KV(dict):
+        def check(self, keys): return all(k in self for k in keys)
+        def get(self, k): return self[k].encode()
+        def set(self, k, v): self[k] = v
+
+    t = TorchDistTransport.__new__(TorchDistTransport)
+    t.rank, t._kv, t._kill_enabled = 2, KV(), True
+    assert not t.kill_requested(3)
+    t.send_kill(2, 7)
+    assert not t.kill_requested(8) and t.kill_requested(7)   # a step-7 signal cannot abort step 8
