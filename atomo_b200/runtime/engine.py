@@ -82,6 +82,7 @@ class FusedEngine:
         self.lr = lr
         self.model = model.to(self.device)
         self.launches_per_step = 0
+        self.nvtx = bool(os.environ.get("ATOMO_NVTX"))   # NVTX ranges around the phases (eager mode)
 
         # ---- plan + symmetric heap -----------------------------------------------------------
         self.layout = FlatLayout.from_module(self.model)
@@ -498,16 +499,28 @@ class FusedEngine:
         """One full step on the current stream (capturable)."""
         C = self.C
         n = 0
+        nvtx = self.nvtx and not torch.cuda.is_current_stream_capturing()
         C.wait_params(self.local_param_flag, self.ctrl, self.timeout_ticks, self.tstats.data_ptr()); n += 1
         if self.is_worker:
             self.flat_grads.zero_()
             if self.bn_arena is not None:
                 self.bn_arena.zero_()          # per-channel accumulators of every fused BN layer
+            if nvtx:
+                torch.cuda.nvtx.range_push("fwd_bwd")
             self._forward_backward()
             n += 4 * self.fused_bn_layers      # stats + apply, backward reduce + apply (csrc/bn_kernels.cu)
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
+                torch.cuda.nvtx.range_push("encode_push")
             n += self._encode_push()
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
         if self.is_ps:
+            if nvtx:
+                torch.cuda.nvtx.range_push("ps_update")
             n += self._ps_update()
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
         C.advance_step(self.ctrl); n += 1
         self.launches_per_step = n
 
@@ -547,6 +560,48 @@ class FusedEngine:
             self._step_body()
         self.step += 1
         return self.loss_buf
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoint / resume (same `model_step_<N>` file for the evaluator + an `_optim` sidecar)
+    def save_checkpoint(self, train_dir: str, step: Optional[int] = None) -> Optional[str]:
+        """PS rank: write the model file the polling evaluator consumes plus a sidecar with the PS momentum,
+        step, LR and RNG seed, so a later run can resume exactly (the reference cannot resume)."""
+        from ..utils import checkpoint as ckpt
+        if not self.is_ps:
+            return None
+        step = (self.step - 1) if step is None else step
+        torch.cuda.synchronize(self.device)
+        path = ckpt.save_model(train_dir, step, self.model)
+        side = {"step": step, "lr": self.lr, "momentum_buffer": self.momentum_buf.detach().cpu(),
+                "ctrl": bytes(self.ctrl.cpu().numpy().tobytes()), "code": self.code, "svd_rank": self.svd_rank}
+        tmp = path + "_optim.tmp"
+        torch.save(side, tmp)
+        os.replace(tmp, path + "_optim")
+        return path
+
+    def load_checkpoint(self, train_dir: str, step: int) -> None:
+        """Collective: every rank calls this with the same ``step``.  Rank 0 restores model + momentum from
+        disk, the parameters are re-broadcast over the heap and every rank's device step / flags jump to
+        ``step + 1``."""
+        from ..utils import checkpoint as ckpt
+        self._barrier()
+        if self.is_ps:
+            ckpt.load_model(train_dir, step, self.model, map_location=self.device)   # in place: params are heap views
+            side_path = ckpt.model_path(train_dir, step) + "_optim"
+            if os.path.exists(side_path):
+                side = torch.load(side_path, map_location="cpu", weights_only=False)
+                self.momentum_buf.copy_(side["momentum_buffer"].to(self.device))
+                if side.get("lr") is not None:
+                    self.set_lr(float(side["lr"]))
+        self._barrier()
+        if self.is_ps and self.world > 1:
+            self.C.param_bcast(self.flat_params, self.t_params_peer, self.params_mc, self.world, self.rank,
+                               self.plan.total_elems)
+        self._barrier()
+        self.step = step + 1
+        self.ctrl_i32[0] = self.step          # Ctrl::step; first_step stays 1 so momentum is not re-initialised
+        self.signals[PARAM_FLAG_SLOT] = self.step
+        self._barrier()
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -594,6 +649,10 @@ def run_p2p_training(args):
     test_loader = torch.utils.data.DataLoader(test_set, batch_size=args.test_batch_size, shuffle=False)
     x0, y0 = loader.next_batch()
     eng.prepare(x0, y0, warmup=0 if args.max_steps < 8 else 3)
+    if getattr(args, "resume", False):
+        last = ckpt.latest_step(args.train_dir)
+        if last is not None:
+            eng.load_checkpoint(args.train_dir, last)   # collective: same directory on every rank
     n_data, base_lr, shrink = len(shard), args.lr, 0
     msg_mb = (eng.plan.factor_bytes_per_worker() + eng.plan.dense_bytes()) / 2 ** 20
     while eng.step <= args.max_steps:
@@ -611,7 +670,7 @@ def run_p2p_training(args):
                 print(master_line(cur, 0.0, eng.lr, 0.0))
         if cur % args.eval_freq == 0:
             if eng.is_ps:
-                ckpt.save_model(args.train_dir, cur, eng.model)
+                eng.save_checkpoint(args.train_dir, cur)
             if eng.is_worker and rank == first:
                 eng.model.eval()
                 tl, a1, a5, nbt, cnt = 0.0, 0.0, 0.0, 0, 0

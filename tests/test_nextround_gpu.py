@@ -1,0 +1,46 @@
+"""GPU tests written after this round's GPU budget was spent: NOT part of `-m gpu`.
+Run them first thing next round:  ATOMO_NEXTROUND=1 python -m pytest tests/test_nextround_gpu.py -q
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.skipif(not (os.environ.get("ATOMO_NEXTROUND") and torch.cuda.is_available()),
+                                reason="unverified GPU tests: set ATOMO_NEXTROUND=1 on a GPU box")
+
+
+def test_engine_checkpoint_resume_roundtrip(tmp_path):
+    from atomo_b200.data import SyntheticImageDataset
+    from atomo_b200.models import build_model
+    from atomo_b200.runtime.engine import FusedEngine
+    torch.cuda.set_device(0)
+    d = str(tmp_path) + "/"
+    x, y = SyntheticImageDataset((1, 28, 28), 10, 512).materialize(32)
+    x, y = x.pin_memory(), y.pin_memory()
+
+    def make():
+        torch.manual_seed(0)
+        return FusedEngine(build_model("LeNet", 10), 0, 1, code="svd", svd_rank=3, lr=0.05, momentum=0.9,
+                           use_graph=False, seed=5)
+
+    a = make()
+    a.prepare(x, y, warmup=0)
+    for _ in range(5):
+        a.train_step(x, y)
+    a.save_checkpoint(d)                       # step 5
+    for _ in range(3):
+        a.train_step(x, y)
+    torch.cuda.synchronize()
+    want = a.flat_params.clone()
+    a.close()
+
+    b = make()
+    b.prepare(x, y, warmup=0)
+    b.load_checkpoint(d, 5)
+    assert b.device_step() == 6
+    for _ in range(3):
+        b.train_step(x, y)
+    torch.cuda.synchronize()
+    assert torch.allclose(b.flat_params, want, rtol=1e-4, atol=1e-5)   # same Philox stream (seed, step, worker)
+    b.close()
