@@ -92,7 +92,6 @@ namespace {
 inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 template <typename T>
 inline T* P(uint64_t v) { return reinterpret_cast<T*>(static_cast<uintptr_t>(v)); }
-inline const float* fptr(const torch::Tensor& t) { return t.defined() && t.numel() ? t.data_ptr<float>() : nullptr; }
 
 void check_cuda_f32(const torch::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
@@ -101,11 +100,6 @@ void check_cuda_f32(const torch::Tensor& t, const char* name) {
 }
 
 // ---------------------------------------------------------------------------------------------- heap
-struct Heap {
-  void* h = nullptr;
-  ~Heap() { if (h) atomo_heap_destroy(h); }
-};
-
 uint64_t heap_create_vmm(int rank, int world, int device, uint64_t bytes, const std::string& job, bool want_mc,
                          double timeout_s) {
   void* h = atomo_heap_create_vmm(rank, world, device, bytes, job.c_str(), want_mc ? 1 : 0, timeout_s);

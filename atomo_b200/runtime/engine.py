@@ -640,7 +640,7 @@ def run_p2p_training(args):
                       momentum=args.momentum, weight_decay=args.weight_decay, nesterov=args.nesterov,
                       ps_mode=args.ps_mode, sampling=args.sampling, prob_rule=args.prob_rule, seed=args.seed,
                       quantization_level=args.quantization_level, bucket_size=args.bucket_size,
-                      entry_budget=args.entry_budget, dtype=args.dtype)
+                      entry_budget=args.entry_budget, dtype=args.dtype, channels_last=(args.dtype == "bf16"))
     first = 0 if args.ps_mode == "colocated" or world == 1 else 1
     nworkers = world - first
     shard = shard_dataset(train_set, max(rank - first, 0), nworkers, seed=args.seed)
@@ -648,7 +648,7 @@ def run_p2p_training(args):
                         pin_memory=True, prefetch=2)
     test_loader = torch.utils.data.DataLoader(test_set, batch_size=args.test_batch_size, shuffle=False)
     x0, y0 = loader.next_batch()
-    eng.prepare(x0, y0, warmup=0 if args.max_steps < 8 else 3)
+    eng.prepare(x0, y0, warmup=2 if args.max_steps < 8 else 3)   # eager warm-up steps (cuDNN autotune) count as steps
     if getattr(args, "resume", False):
         last = ckpt.latest_step(args.train_dir)
         if last is not None:

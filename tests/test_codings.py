@@ -143,3 +143,52 @@ def test_indicators():
     s = torch.linalg.svdvals(a)
     assert nuclear_indicator(a, s) == pytest.approx(float(s.sum()) * math.sqrt(38))
     assert l1_indicator(a) == pytest.approx(float(a.abs().sum()), rel=1e-5)
+
+
+def test_qsgd_word_layout_matches_reference_packing_loop():
+    """Bit-level parity with the reference's packing (qsgd.py:52-78): for each of the floor(64/(2+q)) sections
+    ``neo <<= (2+q); neo |= (sign << q | xi)`` over a (section, word) reshaped array."""
+    import numpy as np
+    q, bucket = 4, 512
+    coder = codings.build("qsgd", quantization_level=q, bucket_size=bucket)
+    g = torch.randn(bucket)
+    u = torch.rand(bucket)
+    code = coder.encode(g, uniforms=u)
+    # independent re-implementation of the reference loop on the same (sign, xi)
+    s = (1 << q) - 1
+    w = g.numpy().astype(np.float64)
+    norm = np.linalg.norm(w.astype(np.float32))
+    a = np.minimum(np.abs(w.astype(np.float32)) / np.float32(norm) * s, s)
+    low = np.floor(a)
+    xi = (low + (u.numpy() < (a - low))).astype(np.uint64)
+    sign = (np.sign(w) + 1).astype(np.uint64)
+    E = 64 // (2 + q)
+    L = (bucket + E - 1) // E
+    pad = E * L - bucket
+    xi = np.pad(xi, (0, pad)); sign = np.pad(sign, (0, pad), constant_values=1)
+    xi, sign = xi.reshape(E, L), sign.reshape(E, L)
+    neo = np.zeros(L, dtype=np.uint64)
+    for i in range(E):
+        neo = (neo << np.uint64(2 + q)) | ((sign[i] << np.uint64(q)) | xi[i])
+    assert np.array_equal(code["words"].numpy().astype(np.uint64)[0], neo)
+
+
+def test_wire_roundtrip_property():
+    from hypothesis import given, settings, strategies as st
+    from atomo_b200.parallel import wire
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.lists(st.tuples(st.integers(1, 7), st.integers(1, 9), st.sampled_from(["float32", "int64", "int32", "uint8"])),
+                    min_size=0, max_size=5), st.integers(-5, 10 ** 6))
+    def check(specs, step):
+        tensors = []
+        for a, b, dt in specs:
+            t = torch.randint(0, 100, (a, b)).to(getattr(torch, dt))
+            tensors.append(t)
+        obj = {"step": step, "codes": [{"t": t, "shape": list(t.shape), "tag": "x"} for t in tensors], "none": None}
+        out = wire.unpack(wire.pack(obj))
+        assert out["step"] == step and out["none"] is None and len(out["codes"]) == len(tensors)
+        for t, c in zip(tensors, out["codes"]):
+            assert torch.equal(c["t"], t) and c["shape"] == list(t.shape) and c["tag"] == "x"
+
+    check()
