@@ -13,8 +13,10 @@ Behavioural parity with ``/root/reference/src/codings/svd.py``:
 Divergences (intentional): odd-length vectors are
 matricized as ``(n, 1)`` instead of crashing, tensors stay ``torch.Tensor``
 (no numpy), the ``fetch_indicator`` path works, and the sampling rule/scheme
-are selectable (``sampling.py``).  On CUDA tensors ``encode`` dispatches to the
-hand-written sm_100a kernels in ``atomo_b200.ops`` when they are built.
+are selectable (``sampling.py``).  This per-tensor class is the oracle and the
+gloo/NCCL-path coder (it runs ``torch.linalg.svd`` on whatever device the
+gradient lives on); the fused engine encodes ALL layers at once with the
+sm_100a kernels of ``csrc/svd_kernels.cu`` and is tested against this class.
 """
 from __future__ import annotations
 
