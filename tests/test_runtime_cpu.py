@@ -89,7 +89,9 @@ def test_checkpoint_layout_and_resume(tmp_path):
 def _run_launcher(extra, timeout=240):
     cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
            "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64"] + extra
-    env = dict(os.environ, ATOMO_HANG_DUMP_S=str(timeout - 20), PYTHONPATH=ROOT)
+    # 2-3 ranks x (8 OpenMP threads) oversubscribe the 8-core CI box: pin the ranks to 2 threads each
+    env = dict(os.environ, ATOMO_HANG_DUMP_S=str(timeout - 20), PYTHONPATH=ROOT, OMP_NUM_THREADS="2",
+               MKL_NUM_THREADS="2")
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
