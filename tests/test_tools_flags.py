@@ -1,0 +1,60 @@
+"""Ops tooling + flag surface."""
+import argparse
+import importlib.util
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_flag_surface_and_defaults():
+    from atomo_b200.utils.flags import add_fit_args, bool_flag
+    a = add_fit_args(argparse.ArgumentParser(), [])
+    ref_defaults = {  # distributed_nn.py:37-80
+        "batch_size": 128, "test_batch_size": 1000, "max_steps": 10000, "epochs": 100, "lr": 0.01, "momentum": 0.5,
+        "lr_shrinkage": 0.95, "no_cuda": False, "seed": 1, "log_interval": 10, "network": "LeNet", "code": "sgd",
+        "bucket_size": 512, "dataset": "MNIST", "comm_type": "Bcast", "eval_freq": 50,
+        "train_dir": "output/models/", "compress": False, "enable_gpu": False, "svd_rank": 0,
+        "quantization_level": 4,
+    }
+    for k, v in ref_defaults.items():
+        assert getattr(a, k) == v, k
+    assert a.num_aggregate == 0  # documented divergence: the flag now has an effect, 0 = all workers
+    # the reference's `type=bool` contract: scripts pass `--enable-gpu=` for False, anything else is True
+    b = add_fit_args(argparse.ArgumentParser(), ["--enable-gpu=", "--compress=yes"])
+    assert b.enable_gpu is False and b.compress is True
+    assert bool_flag("0") is False and bool_flag("False") is False and bool_flag("1") is True
+
+
+def test_cluster_tool_command_map_and_cfg(tmp_path, monkeypatch):
+    cl = _load(os.path.join(ROOT, "tools", "cluster.py"), "cluster_tool")
+    # the reference's command names (pytorch_ec2.py:938-951)
+    for cmd in ("launch", "get_hosts", "shutdown", "kill_all_python", "kill_python", "run_command", "setup_nfs",
+                "list_idle_instances", "list_running_instances", "clean_launch_and_run"):
+        assert cmd in cl.command_map
+    cfg = cl.Cfg({"a": "x", "b": "%(a)s/y", "c": "%(b)s/z"})
+    assert cfg["c"] == "x/y/z"
+    rc, out = cl._run("localhost", "echo hello")
+    assert rc == 0 and "hello" in out
+    monkeypatch.setattr(cl.os.path, "dirname", lambda p: str(tmp_path))
+    args = argparse.Namespace(hosts="n1,n2,n3", hostfile="")
+    assert cl.get_hosts(args) == ["n1", "n2", "n3"]
+    assert open(os.path.join(str(tmp_path), "hosts_address")).read().split() == ["n1", "n2", "n3"]
+    assert "deeplearning-worker2" in open(os.path.join(str(tmp_path), "hosts_alias")).read()
+
+
+def test_data_prepare_and_sv_decay_tools(tmp_path, capsys):
+    from atomo_b200.data.data_prepare import main as prep
+    prep(["--root", str(tmp_path), "--materialize", "8"])
+    assert os.path.exists(os.path.join(str(tmp_path), "mnist_synthetic.pt"))
+    sv = _load(os.path.join(ROOT, "tools", "sv_decay.py"), "sv_decay_tool")
+    rows = sv.main(["--network", "LeNet", "--layer", "conv2.weight", "--steps", "2", "--every", "1",
+                    "--batch-size", "8"])
+    assert len(rows) == 3 and len(rows[0][1]) == 50 and rows[0][1][0] == 1.0  # (500, 50) matricization
