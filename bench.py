@@ -112,6 +112,8 @@ class ClockSampler(threading.Thread):
 
 
 def reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:   # launched under torchrun for N > 1: one line, from rank 0
+        return
     print(json.dumps({
         "impl": "reference",
         "unavailable": "hwang595/ATOMO has no setup.py/pyproject (pip: 'not installable'), is Python-2.7 + mpi4py + "
