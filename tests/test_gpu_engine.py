@@ -190,3 +190,42 @@ def test_subspace_engine_trains(net):
     torch.cuda.synchronize()
     assert eng.error_code() == 0 and float(stats[0]) < first
     eng.close()
+
+
+def test_engine_checkpoint_resume_roundtrip(tmp_path):
+    from atomo_b200.data import SyntheticImageDataset
+    from atomo_b200.models import build_model
+    from atomo_b200.runtime.engine import FusedEngine
+    torch.cuda.set_device(0)
+    d = str(tmp_path) + "/"
+    x, y = SyntheticImageDataset((1, 28, 28), 10, 512).materialize(32)
+    x, y = x.pin_memory(), y.pin_memory()
+
+    def make():
+        torch.manual_seed(0)
+        return FusedEngine(build_model("LeNet", 10), 0, 1, code="sgd", lr=0.05, momentum=0.9,
+                           use_graph=False, seed=5)
+
+    a = make()
+    a.prepare(x, y, warmup=0)
+    for _ in range(5):
+        a.train_step(x, y)
+    a.save_checkpoint(d)                       # step 5
+    for _ in range(3):
+        a.train_step(x, y)
+    torch.cuda.synchronize()
+    want = a.flat_params.clone()
+    a.close()
+
+    b = make()
+    b.prepare(x, y, warmup=0)
+    b.load_checkpoint(d, 5)
+    assert b.device_step() == 6
+    for _ in range(3):
+        b.train_step(x, y)
+    torch.cuda.synchronize()
+    # dense coder: deterministic up to cuDNN's atomics.  (With a sampling coder a 1e-7 difference in a
+    # probability can flip a Bernoulli draw, so resumed runs are statistically, not bitwise, identical:
+    # observed on B200 this round: load/step bookkeeping exact, parameters within 1e-3.)
+    assert torch.allclose(b.flat_params, want, rtol=1e-3, atol=1e-4)
+    b.close()

@@ -379,3 +379,46 @@ def test_fused_bn_matches_stock_ops(C, hw, with_res, relu):
     if with_res:
         bad = ((r.grad.float() - rr.grad).abs() > 2e-2 * float(rr.grad.abs().max()) + 1e-3).float().mean()
         assert float(bad) < 1e-4, float(bad)
+
+
+@pytest.mark.parametrize("W,rank", [(8, 3), (8, 8), (4, 16)])
+def test_ps_update_many_virtual_workers_multi_chunk_K(W, rank):
+    """W 'virtual workers' on one GPU (W arenas, all local): exercises the concatenated-K path of
+    ps_update_kernel with K = sum_w count_w > PS_KC (several K chunks, float4 group gathers, SV reload)."""
+    h = Harness(SHAPES, rank=rank, lr=0.05, momentum=0.9)
+    pl = h.plan
+    dev = h.dev
+    arena = torch.zeros(W * pl.arena_floats, device=dev)
+    grads = [torch.zeros_like(h.grads) for _ in range(W)]
+    t_grads_peer = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64, device=dev)
+    est = torch.zeros_like(h.params)
+    for w in range(W):
+        _fill_grads(h, seed=100 + w)
+        grads[w].copy_(h.grads)
+        C = h.C
+        C.gram(h.grads, h.t_layers, h.t_enc, len(pl.enc_tiles), h.gpart)
+        C.eig_sample(h.t_layers, h.t_ts, h.gpart, h.vsel, h.selcount, h.sigma, arena.data_ptr(), pl.arena_floats,
+                     h.ctrl, None, rank, True, False, False, w, 1024)
+        C.project_push(h.grads, h.t_layers, h.t_enc, len(pl.enc_tiles), h.vsel, h.selcount, arena.data_ptr(),
+                       pl.arena_floats, h.flags.data_ptr(), h.ctrl, w, True)
+        torch.cuda.synchronize()
+        # reference: decode this worker's slots
+        saved = h.arena
+        h.arena = arena[w * pl.arena_floats:(w + 1) * pl.arena_floats]
+        for l in pl.layers:
+            if l.route == 1:
+                c, s, V, U = h.slot(l)
+                h.tall(l, est).add_((U * s) @ V)
+            else:
+                est[l.off:l.off + l.numel] += grads[w][l.off:l.off + l.numel]
+        h.arena = saved
+    assert all(int(h.flags[w]) == 1 for w in range(W))
+    ref_p = h.params - 0.05 * (est / W)          # first step: momentum buffer = gradient
+    h.C.ps_update(h.t_layers, h.t_ps, len(pl.ps_tiles), W, W, 1, h.params, h.mom, h.t_params_peer, 0, t_grads_peer, 0,
+                  arena.data_ptr(), pl.arena_floats, h.flags.data_ptr(), h.t_flag_peer, h.ctrl, int(5e9), 1.0 / W,
+                  min(len(pl.ps_tiles), 296))
+    torch.cuda.synchronize()
+    assert int(h.ctrl.view(torch.int32)[1]) == 0
+    for l in pl.layers:
+        a, b = h.params[l.off:l.off + l.numel], ref_p[l.off:l.off + l.numel]
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-5), (l.shape, float((a - b).abs().max()))
