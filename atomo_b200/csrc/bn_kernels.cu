@@ -9,6 +9,7 @@
 // All tensors are viewed as [R = N*H*W][C] with C % 8 == 0; every access is a 16-byte vector of
 // 8 bf16 channels; statistics are accumulated in fp32.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -50,7 +51,23 @@ bn_stats_kernel(const uint4* __restrict__ x, long long R, int C, float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (rl < RL) {
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
+    // 4 independent 16-byte loads in flight per thread: the per-layer tensors are 2-16 MB (L2 resident right
+    // after the producing conv), so the kernel is latency bound unless every thread keeps several requests open
+    const long long stride = (long long)gridDim.x * RL;
+    long long r = (long long)blockIdx.x * RL + rl;
+    for (; r + 3 * stride < R; r += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(x + (r + k * stride) * CG + cg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(v[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; r < R; r += stride) {
       float f[8];
       unpack8(__ldg(x + r * CG + cg), f);
 #pragma unroll
@@ -133,7 +150,32 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; }
   if (rl < RL) {
-    for (long long r = (long long)blockIdx.x * RL + rl; r < R; r += (long long)gridDim.x * RL) {
+    const long long stride = (long long)gridDim.x * RL;
+    long long r = (long long)blockIdx.x * RL + rl;
+    for (; r + stride < R; r += 2 * stride) {   // 2 rows x 3 tensors = 6 independent 16-byte loads in flight
+      uint4 dv[2], xq[2], yq[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        dv[k] = __ldg(dy + (r + k * stride) * CG + cg);
+        xq[k] = __ldg(x + (r + k * stride) * CG + cg);
+        if (relu) yq[k] = __ldg(y + (r + k * stride) * CG + cg);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float d[8], xv[8];
+        unpack8(dv[k], d);
+        unpack8(xq[k], xv);
+        if (relu) {
+          float yv[8];
+          unpack8(yq[k], yv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = yv[i] > 0.f ? d[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += d[i]; q[i] = fmaf(d[i], (xv[i] - mu[i]) * is[i], q[i]); }
+      }
+    }
+    for (; r < R; r += stride) {
       float d[8], xv[8];
       unpack8(__ldg(dy + r * CG + cg), d);
       unpack8(__ldg(x + r * CG + cg), xv);
@@ -214,11 +256,19 @@ static int bn_grid(long long work_items, int per_block) {
 }
 // reduction kernels: rows handled per thread, chosen so that even the small late layers (R = 2048)
 // launch ~2 waves of CTAs instead of 32 latency-bound ones
+static int g_bn_reduce_ctas = 0;
 static int bn_reduce_grid(long long R, int RL) {
-  long long rpt = R / ((long long)RL * 148 * 4);
-  if (rpt < 1) rpt = 1;
-  if (rpt > 16) rpt = 16;
-  return bn_grid(R, RL * (int)rpt);
+  // Every CTA ends with 2C global atomics, so the grid is capped at a few CTAs per SM (round 1 launched up to
+  // 1024 CTAs of one row per thread for the 2-4 MB layers: ~0.5 M atomics, slower than the 16 MB layers);
+  // the row loops keep 4-6 loads in flight per thread instead.
+  if (g_bn_reduce_ctas == 0) {
+    const char* e = getenv("ATOMO_BN_REDUCE_CTAS");
+    g_bn_reduce_ctas = e != nullptr ? atoi(e) : 296;
+    if (g_bn_reduce_ctas < 1) g_bn_reduce_ctas = 296;
+  }
+  long long g = (R + RL - 1) / RL;
+  if (g > g_bn_reduce_ctas) g = g_bn_reduce_ctas;
+  return (int)(g < 1 ? 1 : g);
 }
 
 void atomo_launch_bn_forward(const void* x, const void* res, void* y, long long R, int C, float* acc,

@@ -20,7 +20,8 @@ from ._ext import load as _load
 
 class _FusedBNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, residual, relu, eps, momentum, acc_fwd, acc_bwd):
+    def forward(ctx, x, weight, bias, running_mean, running_var, residual, relu, eps, momentum, acc_fwd, acc_bwd,
+                grad_sink=None):
         C = _load()
         y = torch.empty_like(x, memory_format=torch.channels_last)
         nch = x.size(1)
@@ -35,6 +36,7 @@ class _FusedBNFn(torch.autograd.Function):
         ctx.relu = relu
         ctx.has_res = residual is not None
         ctx.acc_bwd = acc_bwd
+        ctx.grad_sink = grad_sink
         return y
 
     @staticmethod
@@ -47,10 +49,16 @@ class _FusedBNFn(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
         acc = ctx.acc_bwd if ctx.acc_bwd is not None else torch.empty(2 * nch, dtype=torch.float32, device=x.device)
+        if ctx.grad_sink is not None:
+            # the engine owns the gradient buffers: dgamma / dbeta are written in place by the kernel and autograd
+            # sees no gradient for weight / bias (no AccumulateGrad add kernels for the 2 x #BN vectors)
+            dgamma, dbeta = ctx.grad_sink
+            C.bn_backward(dy, x, y, dx, dres, mean, invstd, weight, acc, dgamma, dbeta, ctx.relu, ctx.acc_bwd is None)
+            return dx, None, None, None, None, dres, None, None, None, None, None, None
         dgamma = torch.empty(nch, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(nch, dtype=torch.float32, device=x.device)
         C.bn_backward(dy, x, y, dx, dres, mean, invstd, weight, acc, dgamma, dbeta, ctx.relu, ctx.acc_bwd is None)
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
 class BNAct(nn.BatchNorm2d):
@@ -59,6 +67,7 @@ class BNAct(nn.BatchNorm2d):
     fused = False
     _acc_fwd = None   # slices of the per-model statistics arena (see enable_fused_bn)
     _acc_bwd = None
+    _grad_sink = None  # (dgamma, dbeta) views the fused backward writes directly (set by the engine)
 
     def _can_fuse(self, x: torch.Tensor, residual: Optional[torch.Tensor]) -> bool:
         if not (self.fused and self.training and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
@@ -77,7 +86,7 @@ class BNAct(nn.BatchNorm2d):
             # num_batches_tracked is only consumed when momentum is None (cumulative average), which the
             # fused path does not take: skipping the per-layer counter kernel saves ~20 launches per step
             return _FusedBNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, residual,
-                                    relu, self.eps, self.momentum, self._acc_fwd, self._acc_bwd)
+                                    relu, self.eps, self.momentum, self._acc_fwd, self._acc_bwd, self._grad_sink)
         out = super().forward(x)
         if residual is not None:
             out = out + residual

@@ -145,6 +145,13 @@ class FusedEngine:
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)  # activations only; weights stay flat views
             bind_parameters(self.model, self.flat_params, self.layout)
+        if self.fused_bn_layers:
+            # the fused BN backward writes dgamma / dbeta straight into the flat gradient buffer (the views that
+            # are these parameters' .grad): no AccumulateGrad add kernels for the 2 x #BN vectors
+            from ..ops.fused_bn import BNAct
+            for m in self.model.modules():
+                if isinstance(m, BNAct) and m.fused and m.weight is not None:
+                    m._grad_sink = (m.weight.grad, m.bias.grad)
 
         # ---- device tables --------------------------------------------------------------------
         dev = self.device

@@ -341,9 +341,11 @@ def test_tcgen05_skinny_gemm_matches_fp32_matmul():
         assert err < 3e-3, err  # tf32 inputs (10-bit mantissa), fp32 accumulate
 
 
-@pytest.mark.parametrize("C,hw,with_res,relu", [(64, 32, False, True), (128, 16, True, True), (512, 4, True, True),
-                                                (256, 8, False, False), (96, 5, True, False)])
-def test_fused_bn_matches_stock_ops(C, hw, with_res, relu):
+@pytest.mark.parametrize("C,hw,with_res,relu,batch", [(64, 32, False, True, 16), (128, 16, True, True, 16),
+                                                      (512, 4, True, True, 16), (256, 8, False, False, 16),
+                                                      (96, 5, True, False, 16), (64, 32, True, True, 128),
+                                                      (512, 4, False, True, 128), (2048, 2, True, True, 8)])
+def test_fused_bn_matches_stock_ops(C, hw, with_res, relu, batch):
     """Fused BN(+residual)(+ReLU) NHWC bf16 kernels vs nn.BatchNorm2d + add + relu (fp32 reference)."""
     import copy
     from atomo_b200.ops.fused_bn import BNAct
@@ -355,8 +357,8 @@ def test_fused_bn_matches_stock_ops(C, hw, with_res, relu):
         bn.bias.uniform_(-0.5, 0.5)
     ref = copy.deepcopy(bn)
     bn.fused = True
-    x32 = torch.randn(16, C, hw, hw, device=dev) * 2 + 0.3
-    r32 = torch.randn(16, C, hw, hw, device=dev)
+    x32 = torch.randn(batch, C, hw, hw, device=dev) * 2 + 0.3
+    r32 = torch.randn(batch, C, hw, hw, device=dev)
     x = x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     r = r32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
     xr = x.detach().float().requires_grad_(True)          # fp32 reference on the same (bf16-rounded) values
@@ -379,6 +381,49 @@ def test_fused_bn_matches_stock_ops(C, hw, with_res, relu):
     if with_res:
         bad = ((r.grad.float() - rr.grad).abs() > 2e-2 * float(rr.grad.abs().max()) + 1e-3).float().mean()
         assert float(bad) < 1e-4, float(bad)
+
+
+def test_fused_bn_graph_capture_and_grad_sinks():
+    """The fused BN must replay inside a CUDA graph (the engine's step is one graph) and dgamma/dbeta must land
+    in the caller's sink (no autograd gradient for weight / bias)."""
+    from atomo_b200.ops.fused_bn import BNAct, enable_fused_bn
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    bn = BNAct(128).to(dev)
+    enable_fused_bn(bn, True)
+    sink = (torch.zeros(128, device=dev), torch.zeros(128, device=dev))
+    bn._grad_sink = sink
+    x = (torch.randn(64, 128, 16, 16, device=dev)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    g = torch.randn(64, 128, 16, 16, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def step():
+        x.grad = None
+        y = bn(x, relu=True)
+        y.backward(g)
+        return y
+    for _ in range(3):
+        y_eager = step().detach().clone()
+    torch.cuda.synchronize()
+    dx_eager, dg_eager = x.grad.clone(), sink[0].clone()
+    assert bn.weight.grad is None and float(dg_eager.abs().sum()) > 0
+    rm = bn.running_mean.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y_static = step()
+    sink[0].zero_()
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(y_static.float(), y_eager.float(), rtol=2e-2, atol=2e-2)   # fp32 atomics reorder
+    assert torch.allclose(x.grad.float(), dx_eager.float(), rtol=1e-2, atol=1e-3)
+    assert torch.allclose(sink[0], dg_eager, rtol=1e-3, atol=1e-3)
+    assert not torch.equal(bn.running_mean, rm)      # the running statistics kept moving under replay
 
 
 @pytest.mark.parametrize("W,rank", [(8, 3), (8, 8), (4, 16)])
