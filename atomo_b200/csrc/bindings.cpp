@@ -61,6 +61,35 @@ void atomo_launch_bn_forward(const void* x, const void* res, void* y, long long 
 void atomo_launch_bn_backward(const void* dy, const void* x, const void* y, void* dx, void* dres, long long R, int C,
                               const float* mean, const float* invstd, const float* gamma, float* acc, float* dgamma,
                               float* dbeta, int relu, int zero_acc, cudaStream_t stream);
+// v2_encode.cu / v2_ps.cu (overlapped, sharded bf16 engine)
+int atomo_v2_unit_bytes();
+int atomo_v2_ctrl_bytes();
+int atomo_v2_enc_smem();
+int atomo_v2_ps_smem();
+int atomo_v2_ps_tile_elems();
+void atomo_v2_launch_encode(const void* units, const void* tiles, int tile0, int ntiles, const long long* gptr,
+                            float* gpart, unsigned int* unit_counters, float* vsel, int* selcount, float* sigma_out,
+                            float* const* arena_peer, int n_owners, long long arena_floats, void* stage,
+                            const void* ctrl, const float* ext_uniforms, float* vprev, int max_sweeps,
+                            int random_sample, int waterfill, int systematic, int worker, int resample_empty,
+                            int flags, cudaStream_t stream);
+void atomo_v2_launch_project(const void* units, const void* tiles, int tile0, int ntiles, const long long* gptr,
+                             const float* vsel, const int* selcount, float* const* arena_peer, int* const* sig_peer,
+                             int n_owners, long long arena_floats, int worker, int group, void* ctrl,
+                             unsigned int* group_counter, int flags, cudaStream_t stream);
+void atomo_v2_launch_ps(const void* units, const void* tiles, int tile0, int ntiles, int W, int nranks, int group,
+                        int final_group, int owner, float* master, float* mom, float* sq, float* sqmax, float* vmom,
+                        float* vsq, float* vsqmax, void* wshadow_mc, void* const* wshadow_peer, float* vparams_local,
+                        float* vparams_mc, float* const* vparams_peer, const float* vgrads_mc,
+                        const float* const* vgrads_peer, const void* const* stage_peer, const float* arenas,
+                        long long arena_floats, int* sig, int* const* sig_peer, void* ctrl,
+                        unsigned int* group_counter, long long timeout, long long* tstats, float inv_w, int grid,
+                        cudaStream_t stream);
+void atomo_v2_launch_wait_params(const int* sig, int n_owners, void* ctrl, long long timeout, long long* tstats,
+                                 cudaStream_t stream);
+void atomo_v2_launch_advance_step(void* ctrl, cudaStream_t stream);
+void atomo_v2_launch_bcast_bytes(const void* src, void* const* peer, void* mc, int nranks, int self, long long nbytes,
+                                 cudaStream_t stream);
 // gemm_kernels.cu
 int atomo_gemm_tile_bytes();
 int atomo_gemm_smem_bytes();
@@ -115,8 +144,11 @@ bool heap_open_ipc(uint64_t h, const std::string& all_handles) {
 }
 
 torch::Tensor tensor_from_ptr(uint64_t ptr, int64_t numel, const std::string& dtype, int device) {
-  auto dt = dtype == "int32" ? torch::kInt32 : dtype == "int64" ? torch::kInt64 : dtype == "uint8" ? torch::kUInt8
-                                                                                                   : torch::kFloat32;
+  auto dt = dtype == "int32"      ? torch::kInt32
+            : dtype == "int64"    ? torch::kInt64
+            : dtype == "uint8"    ? torch::kUInt8
+            : dtype == "bfloat16" ? torch::kBFloat16
+                                  : torch::kFloat32;
   auto opts = torch::TensorOptions().dtype(dt).device(torch::kCUDA, device);
   return torch::from_blob(P<void>(ptr), {numel}, [](void*) {}, opts);
 }
@@ -299,6 +331,51 @@ void entrywise_scatter(const torch::Tensor& idx_ptrs, const torch::Tensor& val_p
                                  timeout_ticks, cur_stream());
 }
 
+// ---------------------------------------------------------------------------------------------- v2 engine
+// Every pointer argument is a raw device address (uint64): the engine keeps the tensors alive.
+void v2_encode(uint64_t units, uint64_t tiles, int tile0, int ntiles, uint64_t gptr, uint64_t gpart, uint64_t counters,
+               uint64_t vsel, uint64_t selcount, uint64_t sigma_out, uint64_t arena_peer, int n_owners,
+               int64_t arena_floats, uint64_t stage, uint64_t ctrl, uint64_t ext_uniforms, uint64_t vprev,
+               int max_sweeps, bool random_sample, bool waterfill, bool systematic, int worker,
+               bool resample_empty, int flags) {
+  atomo_v2_launch_encode(P<const void>(units), P<const void>(tiles), tile0, ntiles, P<const long long>(gptr),
+                         P<float>(gpart), P<unsigned int>(counters), P<float>(vsel), P<int>(selcount),
+                         P<float>(sigma_out), P<float* const>(arena_peer), n_owners, arena_floats, P<void>(stage),
+                         P<const void>(ctrl), P<const float>(ext_uniforms), P<float>(vprev), max_sweeps, random_sample,
+                         waterfill, systematic, worker, resample_empty ? 1 : 0, flags, cur_stream());
+}
+void v2_project(uint64_t units, uint64_t tiles, int tile0, int ntiles, uint64_t gptr, uint64_t vsel, uint64_t selcount,
+                uint64_t arena_peer, uint64_t sig_peer, int n_owners, int64_t arena_floats, int worker, int group,
+                uint64_t ctrl, uint64_t group_counter, int flags) {
+  atomo_v2_launch_project(P<const void>(units), P<const void>(tiles), tile0, ntiles, P<const long long>(gptr),
+                          P<const float>(vsel), P<const int>(selcount), P<float* const>(arena_peer),
+                          P<int* const>(sig_peer), n_owners, arena_floats, worker, group, P<void>(ctrl),
+                          P<unsigned int>(group_counter), flags, cur_stream());
+}
+void v2_ps(uint64_t units, uint64_t tiles, int tile0, int ntiles, int W, int nranks, int group, bool final_group,
+           int owner, uint64_t master, uint64_t mom, uint64_t sq, uint64_t sqmax, uint64_t vmom, uint64_t vsq,
+           uint64_t vsqmax, uint64_t wshadow_mc, uint64_t wshadow_peer, uint64_t vparams_local, uint64_t vparams_mc,
+           uint64_t vparams_peer, uint64_t vgrads_mc, uint64_t vgrads_peer, uint64_t stage_peer, uint64_t arenas,
+           int64_t arena_floats, uint64_t sig, uint64_t sig_peer, uint64_t ctrl, uint64_t group_counter,
+           int64_t timeout, uint64_t tstats, double inv_w, int grid) {
+  TORCH_CHECK(W <= 16, "too many workers for v2_ps");
+  atomo_v2_launch_ps(P<const void>(units), P<const void>(tiles), tile0, ntiles, W, nranks, group, final_group ? 1 : 0,
+                     owner, P<float>(master), P<float>(mom), P<float>(sq), P<float>(sqmax), P<float>(vmom),
+                     P<float>(vsq), P<float>(vsqmax), P<void>(wshadow_mc), P<void* const>(wshadow_peer),
+                     P<float>(vparams_local), P<float>(vparams_mc), P<float* const>(vparams_peer),
+                     P<const float>(vgrads_mc), P<const float* const>(vgrads_peer), P<const void* const>(stage_peer),
+                     P<const float>(arenas), arena_floats, P<int>(sig), P<int* const>(sig_peer), P<void>(ctrl),
+                     P<unsigned int>(group_counter), timeout, P<long long>(tstats), (float)inv_w, grid, cur_stream());
+}
+void v2_wait_params(uint64_t sig, int n_owners, uint64_t ctrl, int64_t timeout, uint64_t tstats) {
+  atomo_v2_launch_wait_params(P<const int>(sig), n_owners, P<void>(ctrl), timeout, P<long long>(tstats), cur_stream());
+}
+void v2_advance_step(uint64_t ctrl) { atomo_v2_launch_advance_step(P<void>(ctrl), cur_stream()); }
+void v2_bcast_bytes(uint64_t src, uint64_t peer, uint64_t mc, int nranks, int self, int64_t nbytes) {
+  atomo_v2_launch_bcast_bytes(P<const void>(src), P<void* const>(peer), P<void>(mc), nranks, self, nbytes,
+                              cur_stream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -347,6 +424,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("qsgd_decode_sum", &qsgd_decode_sum);
   m.def("entrywise_encode", &entrywise_encode);
   m.def("entrywise_scatter", &entrywise_scatter);
+  // v2 engine
+  m.def("v2_encode", &v2_encode);
+  m.def("v2_project", &v2_project);
+  m.def("v2_ps", &v2_ps);
+  m.def("v2_wait_params", &v2_wait_params);
+  m.def("v2_advance_step", &v2_advance_step);
+  m.def("v2_bcast_bytes", &v2_bcast_bytes);
+  m.def("v2_unit_bytes", &atomo_v2_unit_bytes);
+  m.def("v2_ctrl_bytes", &atomo_v2_ctrl_bytes);
+  m.def("v2_enc_smem", &atomo_v2_enc_smem);
+  m.def("v2_ps_smem", &atomo_v2_ps_smem);
+  m.def("v2_ps_tile_elems", &atomo_v2_ps_tile_elems);
   // constants
   m.def("ps_smem_bytes", &atomo_ps_smem_bytes);
   m.def("ps_tile_elems", &atomo_ps_tile_elems);

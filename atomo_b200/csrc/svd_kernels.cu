@@ -248,8 +248,12 @@ eig_sample_kernel(const LayerDesc* __restrict__ layers, const int* __restrict__ 
         }
         __syncthreads();
       }
-      // quadratic convergence: couplings below 1e-3 at the start of a sweep are ~1e-6 after it
-      if (__int_as_float(s_maxrel) < 1e-3f) break;  // shared value, uniform across the CTA
+      // quadratic convergence: couplings below 1e-3 at the start of a sweep are ~1e-6 after it.  Every thread reads
+      // the shared value BEFORE thread 0 may reset it for the next sweep (else a slow warp can leave the loop alone
+      // and desynchronise all later barriers).
+      const float mr = __int_as_float(s_maxrel);
+      __syncthreads();
+      if (mr < 1e-3f) break;
     }
   }
   __syncthreads();

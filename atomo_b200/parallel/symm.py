@@ -121,7 +121,8 @@ class SymmetricHeap:
     def tensor(self, name: str, dtype: torch.dtype = torch.float32, rank: Optional[int] = None) -> torch.Tensor:
         """A torch view of a region (local by default; a peer's copy when ``rank`` is given)."""
         off, nbytes = self._regions[name]
-        names = {torch.float32: "float32", torch.int32: "int32", torch.int64: "int64", torch.uint8: "uint8"}
+        names = {torch.float32: "float32", torch.int32: "int32", torch.int64: "int64", torch.uint8: "uint8",
+                 torch.bfloat16: "bfloat16"}
         esize = torch.empty((), dtype=dtype).element_size()
         return self.C.tensor_from_ptr(self.ptr(rank) + off, nbytes // esize, names[dtype], self.device)
 

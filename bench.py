@@ -47,7 +47,18 @@ def parse():
     ap.add_argument("--code", type=str, default="svd")
     ap.add_argument("--svd-rank", type=int, default=3)
     ap.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ps-mode", type=str, default="colocated", choices=["colocated", "dedicated"])
+    ap.add_argument("--ps-mode", type=str, default="sharded", choices=["sharded", "colocated", "dedicated"],
+                    help="sharded: every GPU trains and owns 1/N of the PS tiles (default); colocated: rank 0 owns "
+                         "the whole PS and also trains; dedicated: rank 0 only serves (the reference's topology)")
+    ap.add_argument("--engine", type=str, default="auto", choices=["auto", "shadow", "fused"],
+                    help="shadow = overlapped sharded bf16 engine (runtime/shadow_engine.py); fused = round-1 "
+                         "fp32-flat engine (runtime/engine.py: fp32 runs, qsgd / terngrad / entrywise)")
+    ap.add_argument("--groups", type=int, default=4, help="backward groups of the shadow engine")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false", default=True)
+    ap.add_argument("--optimizer", type=str, default="sgd", choices=["sgd", "adam"])
+    ap.add_argument("--ps-grid", type=int, default=0)
+    ap.add_argument("--no-warm-start", dest="warm_start", action="store_false", default=True)
+    ap.add_argument("--max-sweeps", type=int, default=3)
     ap.add_argument("--sampling", type=str, default="bernoulli")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
@@ -151,11 +162,23 @@ def main():
     torch.backends.cudnn.benchmark = args.cudnn_benchmark
     ncls = 1000 if args.dataset == "ImageNet" else 10
     model = build_model(args.network, ncls, args.dataset)
-    eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
-                      ps_mode=args.ps_mode, sampling=args.sampling, dtype=args.dtype, channels_last=args.channels_last,
-                      use_graph=not args.no_graph, seed=1, timeout_s=60.0, subspace={"auto": "auto", "on": True, "off": False}[args.subspace],
-                      fused_bn={"auto": "auto", "on": True, "off": False}[args.fused_bn],
-                      quantization_level=args.quantization_level, entry_budget=args.entry_budget)
+    engine = args.engine
+    if engine == "auto":
+        engine = "shadow" if (args.dtype == "bf16" and args.code in ("svd", "sgd") and args.channels_last) else "fused"
+    if engine == "shadow":
+        from atomo_b200.runtime.shadow_engine import ShadowEngine
+        eng = ShadowEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr,
+                           momentum=args.momentum, ps_mode=args.ps_mode, sampling=args.sampling,
+                           use_graph=not args.no_graph, seed=1, timeout_s=60.0, groups=args.groups,
+                           overlap=args.overlap, optimizer=args.optimizer, fused_bn=args.fused_bn != "off",
+                           ps_grid=args.ps_grid, warm_start=args.warm_start, max_sweeps=args.max_sweeps)
+    else:
+        ps_mode = "colocated" if args.ps_mode == "sharded" else args.ps_mode
+        eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,
+                          ps_mode=ps_mode, sampling=args.sampling, dtype=args.dtype, channels_last=args.channels_last,
+                          use_graph=not args.no_graph, seed=1, timeout_s=60.0, subspace={"auto": "auto", "on": True, "off": False}[args.subspace],
+                          fused_bn={"auto": "auto", "on": True, "off": False}[args.fused_bn],
+                          quantization_level=args.quantization_level, entry_budget=args.entry_budget)
     shape = input_shape(args.network, args.dataset)
     ds = SyntheticImageDataset(shape, ncls, 50000, seed=rank)
     nbatches = 8
@@ -165,7 +188,8 @@ def main():
     torch.cuda.reset_peak_memory_stats(dev)
     base_mem = torch.cuda.memory_allocated(dev)
     eng.prepare(host_x[0], host_y[0], warmup=max(args.warmup, 3))
-    work_mb = (torch.cuda.max_memory_allocated(dev) - base_mem) / 2 ** 20 + 3 * eng.plan.total_elems * 4 / 2 ** 20
+    state_mb = (3 * eng.plan.total_elems * 4 if engine == "fused" else 10 * eng.plan.w_total) / 2 ** 20
+    work_mb = (torch.cuda.max_memory_allocated(dev) - base_mem) / 2 ** 20 + state_mb
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -255,7 +279,9 @@ def main():
     err = 0
 
     if rank == 0:
-        par = ("ps+%dworkers(colocated)" % nworkers) if args.ps_mode == "colocated" else ("ps+%dworkers" % nworkers)
+        pm = eng.ps_mode
+        par = {"sharded": "%dworkers+sharded-ps(every GPU trains and owns 1/%d of the PS)" % (nworkers, world),
+               "colocated": "ps+%dworkers(colocated)" % nworkers, "dedicated": "ps+%dworkers" % nworkers}[pm]
         out = {
             "metric": metric_name(args), "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -264,11 +290,13 @@ def main():
             "config": {"model": args.network, "global_batch": imgs_per_step, "per_worker_batch": args.batch_size,
                        "seq_len": None, "image": list(shape), "parallelism": par, "code": args.code,
                        "svd_rank": args.svd_rank, "sampling": args.sampling, "dataset_shape": args.dataset,
-                       "subspace_route_layers": len(eng.plan.ext.layers) if eng.plan.ext else 0,
+                       "engine": engine, "groups": getattr(eng, "G", 1), "overlap": getattr(eng, "overlap", False),
+                       "subspace_route_layers": (len(eng.plan.ext.layers) if eng.plan.ext else 0) if engine == "fused" else 0,
+                       "coded_units": getattr(eng.plan, "n_coded", None),
                        "fused_bn_layers": eng.fused_bn_layers, "cuda_graph": not args.no_graph,
                        "heap": eng.heap.mode, "nvls_multicast": eng.heap.has_multicast,
                        "l2": "no explicit flush: per-step working set %.0f MB > 126 MB L2" % work_mb,
-                       "optimizer": "momentum-SGD fused in PS kernel", "final_loss": round(losses[-1], 4),
+                       "optimizer": "%s fused in PS kernel" % ("momentum-SGD" if args.optimizer == "sgd" else "Adam"), "final_loss": round(losses[-1], 4),
                        "device_error": err},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "ms_per_step": round(ms_e2e / args.steps, 4),

@@ -15,7 +15,7 @@ here = os.path.dirname(os.path.abspath(__file__))
 src = os.path.join("atomo_b200", "csrc")
 sources = [os.path.join(src, f) for f in (
     "bindings.cpp", "symm_heap.cpp", "svd_kernels.cu", "ps_kernels.cu", "qsgd_kernels.cu",
-    "entrywise_kernels.cu", "ext_kernels.cu", "gemm_kernels.cu", "bn_kernels.cu")]
+    "entrywise_kernels.cu", "ext_kernels.cu", "gemm_kernels.cu", "bn_kernels.cu", "v2_encode.cu", "v2_ps.cu")]
 
 nvcc_flags = ["-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
               "-gencode", "arch=compute_100a,code=sm_100a"]
