@@ -252,7 +252,8 @@ __device__ void eig_sample_unit(const EncArgs& a, const Unit2& u, int unit_id, f
   __syncthreads();
   const float gmax = s_gmax;
   if (n > 1 && gmax > 0.f) {
-    const int sweeps = a.max_sweeps > 0 ? min(a.max_sweeps, MAX_SWEEPS2) : MAX_SWEEPS2;
+    // warm: a.max_sweeps refinement sweeps track the slowly drifting basis; cold (first step / periodic reset): full solve
+    const int sweeps = (warm && a.max_sweeps > 0) ? min(a.max_sweeps, MAX_SWEEPS2) : MAX_SWEEPS2;
     for (int sweep = 0; sweep < sweeps; ++sweep) {
       if (tid == 0) s_maxrel = 0;
       __syncthreads();

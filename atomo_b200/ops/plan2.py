@@ -185,10 +185,13 @@ class Plan2:
 
 def default_groups(shapes: Sequence[Sequence[int]], n_groups: int) -> List[int]:
     """Assign parameters to backward groups.  ``parameters()`` order ~ forward order, so the LAST parameters
-    form group 0 (their gradients exist first).  Walking from the end, group ``g`` closes once the share of
-    weight elements still to come drops below ``0.5 * 0.3**g``: the early groups are large (their encode /
-    push / PS work hides behind the remaining backward), the final group — the first layers, whose update sits
-    on the critical path before the next forward — is a few percent of the model.  A 1-D parameter (BN, bias)
+    form group 0 (their gradients exist first).
+
+    What matters is what is left on the critical path after the last ``wgrad``: the encode -> project -> PS chain
+    of the FINAL group.  So the final group is only the first weight tensor of the network (for the CNNs here the
+    3-channel stem, which travels dense: a staging copy + two PS tiles), the group before it is the next few
+    percent of the weights (its chain hides behind the stem's backward), and the early groups — where almost all
+    bytes are — close once the share still to come drops below ``0.5 * 0.3**g``.  A 1-D parameter (BN, bias)
     joins the group of the weight tensor that precedes it in forward order (its gradient exists earlier)."""
     numels = []
     for s in shapes:
@@ -198,13 +201,18 @@ def default_groups(shapes: Sequence[Sequence[int]], n_groups: int) -> List[int]:
         numels.append(n if len(s) >= 2 else 0)
     total = sum(numels) or 1
     n_groups = max(1, min(n_groups, MAX_GROUPS))
+    w_idx = [i for i, n in enumerate(numels) if n > 0]
     groups = [0] * len(shapes)
+    reserve_last = n_groups >= 3 and len(w_idx) >= n_groups
+    body = n_groups - 1 if reserve_last else n_groups
     acc, g = 0, 0
     for i in range(len(shapes) - 1, -1, -1):
         groups[i] = g
         acc += numels[i]
-        if numels[i] > 0 and g < n_groups - 1 and (total - acc) / total <= 0.5 * 0.3 ** g:
+        if numels[i] > 0 and g < body - 1 and (total - acc) / total <= 0.5 * 0.3 ** g:
             g += 1
+    if reserve_last:
+        groups[w_idx[0]] = g + 1
     last_w = None
     for i, s in enumerate(shapes):
         if len(s) >= 2:

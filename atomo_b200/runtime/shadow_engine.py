@@ -50,12 +50,13 @@ class ShadowEngine:
     def __init__(self, model: nn.Module, rank: int = 0, world: int = 1, code: str = "svd", svd_rank: int = 3,
                  lr: float = 0.01, momentum: float = 0.0, weight_decay: float = 0.0, nesterov: bool = False,
                  dampening: float = 0.0, optimizer: str = "sgd", betas=(0.9, 0.999), eps: float = 1e-8,
-                 amsgrad: bool = False, ps_mode: str = "sharded", groups: int = 4, sampling: str = "bernoulli",
+                 amsgrad: bool = False, ps_mode: str = "sharded", groups: int = 5, sampling: str = "bernoulli",
                  prob_rule: str = "reference", random_sample: bool = True, seed: int = 1, use_graph: bool = True,
                  group=None, multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
                  criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None,
                  ps_grid: int = 0, overlap: bool = True, fused_bn: bool = True, num_aggregate: int = 0,
-                 warm_start: bool = True, max_sweeps: int = 3, resample_empty: bool = False):
+                 warm_start: bool = True, max_sweeps: int = 1, main_priority: int = 0,
+                 side_priority: int = -1, resample_empty: bool = False):
         self.C = load_ext()
         C = self.C
         assert C.v2_unit_bytes() == P2.UNIT_BYTES and C.v2_ctrl_bytes() == P2.CTRL2_BYTES
@@ -234,8 +235,9 @@ class ShadowEngine:
         self.static_x = self.static_y = self.graph = None
 
         # ---- streams / events --------------------------------------------------------------------------------
-        self.s_enc = torch.cuda.Stream(device=dev, priority=-1)
-        self.s_ps = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_enc = torch.cuda.Stream(device=dev, priority=side_priority)
+        self.s_ps = torch.cuda.Stream(device=dev, priority=side_priority)
+        self.s_main = torch.cuda.Stream(device=dev, priority=main_priority)   # warm-up + capture stream
         self.ev_ready = [torch.cuda.Event() for _ in range(self.G)]
         self.ev_push = [torch.cuda.Event() for _ in range(self.G)]
         self.ev_enc_done, self.ev_ps_done = torch.cuda.Event(), torch.cuda.Event()
@@ -405,7 +407,7 @@ class ShadowEngine:
         self.static_x.copy_(x_example)
         self.static_y.copy_(y_example)
         self.model.train()
-        s = torch.cuda.Stream(device=self.device)
+        s = self.s_main
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -417,7 +419,7 @@ class ShadowEngine:
             self.graph = torch.cuda.CUDAGraph()
             self._capturing = True
             try:
-                with torch.cuda.graph(self.graph):
+                with torch.cuda.graph(self.graph, stream=self.s_main):
                     self._step_body()
             finally:
                 self._capturing = False

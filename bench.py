@@ -53,12 +53,14 @@ def parse():
     ap.add_argument("--engine", type=str, default="auto", choices=["auto", "shadow", "fused"],
                     help="shadow = overlapped sharded bf16 engine (runtime/shadow_engine.py); fused = round-1 "
                          "fp32-flat engine (runtime/engine.py: fp32 runs, qsgd / terngrad / entrywise)")
-    ap.add_argument("--groups", type=int, default=4, help="backward groups of the shadow engine")
+    ap.add_argument("--groups", type=int, default=5, help="backward groups of the shadow engine")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false", default=True)
     ap.add_argument("--optimizer", type=str, default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--ps-grid", type=int, default=0)
+    ap.add_argument("--main-priority", type=int, default=0)
+    ap.add_argument("--side-priority", type=int, default=-1)
     ap.add_argument("--no-warm-start", dest="warm_start", action="store_false", default=True)
-    ap.add_argument("--max-sweeps", type=int, default=3)
+    ap.add_argument("--max-sweeps", type=int, default=1)
     ap.add_argument("--sampling", type=str, default="bernoulli")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-channels-last", dest="channels_last", action="store_false", default=True,
@@ -171,7 +173,8 @@ def main():
                            momentum=args.momentum, ps_mode=args.ps_mode, sampling=args.sampling,
                            use_graph=not args.no_graph, seed=1, timeout_s=60.0, groups=args.groups,
                            overlap=args.overlap, optimizer=args.optimizer, fused_bn=args.fused_bn != "off",
-                           ps_grid=args.ps_grid, warm_start=args.warm_start, max_sweeps=args.max_sweeps)
+                           ps_grid=args.ps_grid, warm_start=args.warm_start, max_sweeps=args.max_sweeps,
+                           main_priority=args.main_priority, side_priority=args.side_priority)
     else:
         ps_mode = "colocated" if args.ps_mode == "sharded" else args.ps_mode
         eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr, momentum=args.momentum,

@@ -78,15 +78,17 @@ def test_every_element_is_covered_exactly_once(net, owners):
 
 def test_groups_follow_backward_order_and_the_last_one_is_small():
     shapes = _shapes("ResNet18")
-    g = P.default_groups(shapes, 4)
+    g = P.default_groups(shapes, 5)
     w = [gi for gi, s in zip(g, shapes) if len(s) >= 2]
-    assert w == sorted(w, reverse=True) and w[-1] == 0 and w[0] == 3
-    pl = P.build_plan2(shapes, "svd", 3, n_groups=4)
+    assert w == sorted(w, reverse=True) and w[-1] == 0 and w[0] == 4
+    assert w.count(4) == 1                      # the final group is the stem alone (dense: no eig on the tail)
+    pl = P.build_plan2(shapes, "svd", 3, n_groups=5)
     share = [0] * pl.n_groups
     for q in pl.params:
         if q.is_w:
             share[q.group] += q.numel
-    assert share[0] > 0.5 * sum(share) and share[-1] < 0.06 * sum(share)
+    assert share[0] > 0.5 * sum(share) and share[-1] < 0.001 * sum(share) and share[-2] < 0.06 * sum(share)
+    assert all(u.kind in (P.KIND_DENSE16, P.KIND_VEC) for u in pl.units if u.group == pl.n_groups - 1)
     # a BN vector rides in the group of the conv that precedes it
     for i, s in enumerate(shapes):
         if len(s) == 1 and i > 0:
