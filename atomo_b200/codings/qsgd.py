@@ -12,6 +12,10 @@ Behavioural parity with ``/root/reference/src/codings/qsgd.py``:
   bucket) with section 0 in the most significant bits; each element is
   ``(sign+1) << q | level`` (qsgd.py:52-78).
 
+TernGrad differences from the reference, on purpose: the clip limit ``2.5*std`` is taken over the WHOLE tensor
+(not per bucket) and the per-bucket L-inf norm is taken AFTER clipping, so a clipped element quantizes to the top
+level instead of overflowing it.
+
 Fixed defects: stochastic rounding is *unbiased* (round up with
 probability ``frac``; the reference rounds up with ``1-frac``), the level never
 overflows into the sign bits, and buckets need not divide the tensor (the tail
@@ -66,6 +70,10 @@ class QSGD(Coding):
     def _bucketize(self, flat: torch.Tensor):
         n = flat.numel()
         bucket = self._bucket_size if self._bucket_size > 0 else max(n, 1)
+        # a tensor smaller than one bucket (biases, BN vectors, a 10-way fc bias) is ONE bucket of its own length:
+        # padding it to 512 elements would send 416 B for a 40 B tensor (the reference's np.split gives
+        # ceil(n/512) short buckets, qsgd.py:32-40)
+        bucket = max(1, min(bucket, n))
         nb = (n + bucket - 1) // bucket
         padded = torch.zeros(nb * bucket, dtype=torch.float32, device=flat.device)
         padded[:n] = flat

@@ -72,11 +72,12 @@ void atomo_v2_launch_encode(const void* units, const void* tiles, int tile0, int
                             float* const* arena_peer, int n_owners, long long arena_floats, void* stage,
                             const void* ctrl, const float* ext_uniforms, float* vprev, int max_sweeps,
                             int random_sample, int waterfill, int systematic, int worker, int resample_empty,
-                            int flags, cudaStream_t stream);
+                            int flags, long long* tstats, int group, cudaStream_t stream);
 void atomo_v2_launch_project(const void* units, const void* tiles, int tile0, int ntiles, const long long* gptr,
                              const float* vsel, const int* selcount, float* const* arena_peer, int* const* sig_peer,
                              int n_owners, long long arena_floats, int worker, int group, void* ctrl,
-                             unsigned int* group_counter, int flags, cudaStream_t stream);
+                             unsigned int* group_counter, int flags, long long* tstats, int final_group, int timed,
+                             cudaStream_t stream);
 void atomo_v2_launch_ps(const void* units, const void* tiles, int tile0, int ntiles, int W, int nranks, int group,
                         int final_group, int owner, float* master, float* mom, float* sq, float* sqmax, float* vmom,
                         float* vsq, float* vsqmax, void* wshadow_mc, void* const* wshadow_peer, float* vparams_local,
@@ -337,20 +338,22 @@ void v2_encode(uint64_t units, uint64_t tiles, int tile0, int ntiles, uint64_t g
                uint64_t vsel, uint64_t selcount, uint64_t sigma_out, uint64_t arena_peer, int n_owners,
                int64_t arena_floats, uint64_t stage, uint64_t ctrl, uint64_t ext_uniforms, uint64_t vprev,
                int max_sweeps, bool random_sample, bool waterfill, bool systematic, int worker,
-               bool resample_empty, int flags) {
+               bool resample_empty, int flags, uint64_t tstats, int group) {
   atomo_v2_launch_encode(P<const void>(units), P<const void>(tiles), tile0, ntiles, P<const long long>(gptr),
                          P<float>(gpart), P<unsigned int>(counters), P<float>(vsel), P<int>(selcount),
                          P<float>(sigma_out), P<float* const>(arena_peer), n_owners, arena_floats, P<void>(stage),
                          P<const void>(ctrl), P<const float>(ext_uniforms), P<float>(vprev), max_sweeps, random_sample,
-                         waterfill, systematic, worker, resample_empty ? 1 : 0, flags, cur_stream());
+                         waterfill, systematic, worker, resample_empty ? 1 : 0, flags, P<long long>(tstats), group,
+                         cur_stream());
 }
 void v2_project(uint64_t units, uint64_t tiles, int tile0, int ntiles, uint64_t gptr, uint64_t vsel, uint64_t selcount,
                 uint64_t arena_peer, uint64_t sig_peer, int n_owners, int64_t arena_floats, int worker, int group,
-                uint64_t ctrl, uint64_t group_counter, int flags) {
+                uint64_t ctrl, uint64_t group_counter, int flags, uint64_t tstats, bool final_group, bool timed) {
   atomo_v2_launch_project(P<const void>(units), P<const void>(tiles), tile0, ntiles, P<const long long>(gptr),
                           P<const float>(vsel), P<const int>(selcount), P<float* const>(arena_peer),
                           P<int* const>(sig_peer), n_owners, arena_floats, worker, group, P<void>(ctrl),
-                          P<unsigned int>(group_counter), flags, cur_stream());
+                          P<unsigned int>(group_counter), flags, P<long long>(tstats), final_group ? 1 : 0,
+                          timed ? 1 : 0, cur_stream());
 }
 void v2_ps(uint64_t units, uint64_t tiles, int tile0, int ntiles, int W, int nranks, int group, bool final_group,
            int owner, uint64_t master, uint64_t mom, uint64_t sq, uint64_t sqmax, uint64_t vmom, uint64_t vsq,

@@ -53,6 +53,8 @@ struct EncArgs {
   float* vprev;                // [n_coded][64*64] eigenbasis of the previous step (warm start), or nullptr
   int max_sweeps;              // Jacobi sweep cap (any complete orthonormal basis keeps the estimator unbiased)
   int flags;                   // bit 0: load tiles with plain loads instead of TMA bulk copies
+  long long* tstats;           // device-side phase accounting (see runtime/shadow_engine.py: phase_stats)
+  int group;
   EncCfg cfg;
 };
 
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_encode_kernel(const EncArgs a)
   const Unit2 u = a.units[t.unit];
   const int tid = threadIdx.x;
   const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(a.gptr[u.pidx]) + u.g_off;
+  if (blockIdx.x == 0 && tid == 0 && a.tstats != nullptr) a.tstats[9 + a.group] = globaltimer_ns();
 
   if (u.kind == KIND_DENSE16) {
     // staging copy of a dense bf16 gradient into the symmetric heap (the PS owners pull it from there)
@@ -561,6 +564,9 @@ struct ProjArgs {
   Ctrl2* ctrl;
   unsigned int* group_counter;
   int flags;
+  long long* tstats;
+  int final_group;
+  int timed;          // 1 when an encode launch of this group stamped its start time
 };
 
 constexpr int PROJ_SMEM = ENC_HDR + ENC_TILE_BYTES + V2_MAX_COLS * V2_RCAP_MAX * 4;
@@ -661,6 +667,11 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs 
       const int step = a.ctrl->step;
       for (int o = 0; o < a.n_owners; ++o)
         st_release_sys(a.sig_peer[o] + SIG_PUSH + a.group * MAX_WORKERS + a.worker, step);
+      if (a.tstats != nullptr) {
+        const long long now = globaltimer_ns();
+        if (a.timed) a.tstats[5] += now - a.tstats[9 + a.group];      // encode + project of this group
+        if (a.final_group) a.tstats[8] += now - a.tstats[6];          // step start -> last push published
+      }
     }
   }
 }
@@ -685,7 +696,7 @@ void atomo_v2_launch_encode(const void* units, const void* tiles, int tile0, int
                             float* const* arena_peer, int n_owners, long long arena_floats, void* stage,
                             const void* ctrl, const float* ext_uniforms, float* vprev, int max_sweeps,
                             int random_sample, int waterfill, int systematic, int worker, int resample_empty,
-                            int flags, cudaStream_t stream) {
+                            int flags, long long* tstats, int group, cudaStream_t stream) {
   if (ntiles <= 0) return;
   static bool attr = false;
   if (!attr) {
@@ -698,7 +709,7 @@ void atomo_v2_launch_encode(const void* units, const void* tiles, int tile0, int
   a.unit_counters = unit_counters; a.vsel = vsel; a.selcount = selcount; a.sigma_out = sigma_out;
   a.arena_peer = arena_peer; a.n_owners = n_owners; a.arena_floats = arena_floats;
   a.stage = (__nv_bfloat16*)stage; a.ctrl = (const Ctrl2*)ctrl; a.ext_uniforms = ext_uniforms;
-  a.vprev = vprev; a.max_sweeps = max_sweeps; a.flags = flags;
+  a.vprev = vprev; a.max_sweeps = max_sweeps; a.flags = flags; a.tstats = tstats; a.group = group;
   a.cfg = EncCfg{random_sample, waterfill, systematic, worker, resample_empty};
   v2_encode_kernel<<<ntiles, ENC_THREADS, ENC_SMEM, stream>>>(a);
 }
@@ -706,7 +717,8 @@ void atomo_v2_launch_encode(const void* units, const void* tiles, int tile0, int
 void atomo_v2_launch_project(const void* units, const void* tiles, int tile0, int ntiles, const long long* gptr,
                              const float* vsel, const int* selcount, float* const* arena_peer, int* const* sig_peer,
                              int n_owners, long long arena_floats, int worker, int group, void* ctrl,
-                             unsigned int* group_counter, int flags, cudaStream_t stream) {
+                             unsigned int* group_counter, int flags, long long* tstats, int final_group, int timed,
+                             cudaStream_t stream) {
   if (ntiles <= 0) {
     v2_signal_kernel<<<1, 32, 0, stream>>>(sig_peer, n_owners, group, worker, (const Ctrl2*)ctrl);
     return;
@@ -721,7 +733,7 @@ void atomo_v2_launch_project(const void* units, const void* tiles, int tile0, in
   a.units = (const Unit2*)units; a.tiles = (const Tile2*)tiles + tile0; a.gptr = gptr; a.vsel = vsel;
   a.selcount = selcount; a.arena_peer = arena_peer; a.sig_peer = sig_peer; a.n_owners = n_owners;
   a.arena_floats = arena_floats; a.worker = worker; a.group = group; a.ctrl = (Ctrl2*)ctrl;
-  a.group_counter = group_counter; a.flags = flags;
+  a.group_counter = group_counter; a.flags = flags; a.tstats = tstats; a.final_group = final_group; a.timed = timed;
   v2_project_kernel<<<ntiles, ENC_THREADS, PROJ_SMEM, stream>>>(a);
 }
 

@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
       if (a.final_group)
         for (int r = 0; r < a.nranks; ++r) st_release_sys(a.sig_peer[r] + SIG_PARAM + a.owner, step + 1);
       if (a.tstats != nullptr) {
+        const long long now = globaltimer_ns();
         a.tstats[0] += t_ready - t_enter;
-        a.tstats[1] += globaltimer_ns() - t_ready;
+        a.tstats[1] += now - t_ready;
         a.tstats[2] += 1;
+        if (a.final_group) a.tstats[7] += now - a.tstats[6];   // step start -> this owner's parameters published
       }
     }
   }
@@ -428,7 +430,11 @@ __global__ void v2_wait_params_kernel(const int* sig, int n_owners, Ctrl2* ctrl,
     if (!spin_wait_ge(sig + SIG_PARAM + threadIdx.x, ctrl->step, timeout)) atomicOr(&ctrl->error, ERR2_WAIT_PARAM);
   }
   __syncthreads();
-  if (threadIdx.x == 0 && tstats != nullptr) { tstats[3] += globaltimer_ns() - t0; tstats[4] += 1; }
+  if (threadIdx.x == 0 && tstats != nullptr) {
+    const long long now = globaltimer_ns();
+    tstats[3] += now - t0; tstats[4] += 1;
+    tstats[6] = now;                                             // step start stamp
+  }
 }
 
 __global__ void v2_advance_step_kernel(Ctrl2* ctrl) {

@@ -571,19 +571,24 @@ class FusedEngine:
     # ------------------------------------------------------------------------------------------
     # checkpoint / resume (same `model_step_<N>` file for the evaluator + an `_optim` sidecar)
     def save_checkpoint(self, train_dir: str, step: Optional[int] = None) -> Optional[str]:
-        """PS rank: write the model file the polling evaluator consumes plus a sidecar with the PS momentum,
-        step, LR and RNG seed, so a later run can resume exactly (the reference cannot resume)."""
+        """Call on every rank.  The FIRST TRAINING rank writes the model file the polling evaluator consumes: its
+        parameters are the PS's (multicast every step) and its BatchNorm running statistics are real — a PS that
+        never runs a forward pass (``ps_mode='dedicated'``) would save untrained BN buffers, which is why the
+        reference kept PS checkpointing off for ResNet (sync_replicas_master_nn.py:228-230).  The PS rank writes the
+        ``_optim`` sidecar (momentum, step, LR, RNG seed) so a later run can resume exactly."""
         from ..utils import checkpoint as ckpt
-        if not self.is_ps:
-            return None
         step = (self.step - 1) if step is None else step
         torch.cuda.synchronize(self.device)
-        path = ckpt.save_model(train_dir, step, self.model)
-        side = {"step": step, "lr": self.lr, "momentum_buffer": self.momentum_buf.detach().cpu(),
-                "ctrl": bytes(self.ctrl.cpu().numpy().tobytes()), "code": self.code, "svd_rank": self.svd_rank}
-        tmp = path + "_optim.tmp"
-        torch.save(side, tmp)
-        os.replace(tmp, path + "_optim")
+        path = None
+        if self.rank == self.first_worker:
+            path = ckpt.save_model(train_dir, step, self.model)
+        if self.is_ps:
+            side_path = ckpt.model_path(train_dir, step) + "_optim"
+            os.makedirs(os.path.dirname(side_path) or ".", exist_ok=True)
+            side = {"step": step, "lr": self.lr, "momentum_buffer": self.momentum_buf.detach().cpu(),
+                    "ctrl": bytes(self.ctrl.cpu().numpy().tobytes()), "code": self.code, "svd_rank": self.svd_rank}
+            torch.save(side, side_path + ".tmp")
+            os.replace(side_path + ".tmp", side_path)
         return path
 
     def load_checkpoint(self, train_dir: str, step: int) -> None:
@@ -620,85 +625,6 @@ class FusedEngine:
 
 # ----------------------------------------------------------------------------------------------
 def run_p2p_training(args):
-    """``--backend p2p`` entry of the launcher: every GPU trains, GPU 0 also hosts the PS."""
-    import time
-
-    from ..data import DataLoader, build_datasets, shard_dataset
-    from ..models import build_model
-    from ..utils import checkpoint as ckpt
-    from ..utils.logging import master_line, test_line, worker_line
-    from .nn_ops import accuracy
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1 and not dist.is_initialized():
-        os.environ.setdefault("MASTER_ADDR", args.master_addr)
-        os.environ.setdefault("MASTER_PORT", str(args.master_port))
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    torch.manual_seed(args.seed)  # identical init on every rank; rank 0's copy is broadcast anyway
-    train_set, test_set, num_classes = build_datasets(
-        args.dataset, args.data_root, synthetic=args.synthetic, seed=args.seed,
-        train_len=args.train_len or None, test_len=args.test_len or None)
-    model = build_model(args.network, num_classes, args.dataset)
-    eng = FusedEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr,
-                      momentum=args.momentum, weight_decay=args.weight_decay, nesterov=args.nesterov,
-                      ps_mode=args.ps_mode, sampling=args.sampling, prob_rule=args.prob_rule, seed=args.seed,
-                      quantization_level=args.quantization_level, bucket_size=args.bucket_size,
-                      entry_budget=args.entry_budget, dtype=args.dtype, channels_last=(args.dtype == "bf16"))
-    first = 0 if args.ps_mode == "colocated" or world == 1 else 1
-    nworkers = world - first
-    shard = shard_dataset(train_set, max(rank - first, 0), nworkers, seed=args.seed)
-    loader = DataLoader(shard, batch_size=args.batch_size, shuffle=True, seed=args.seed + rank, drop_last=True,
-                        pin_memory=True, prefetch=2)
-    test_loader = torch.utils.data.DataLoader(test_set, batch_size=args.test_batch_size, shuffle=False)
-    x0, y0 = loader.next_batch()
-    eng.prepare(x0, y0, warmup=2 if args.max_steps < 8 else 3)   # eager warm-up steps (cuDNN autotune) count as steps
-    if getattr(args, "resume", False):
-        last = ckpt.latest_step(args.train_dir)
-        if last is not None:
-            eng.load_checkpoint(args.train_dir, last)   # collective: same directory on every rank
-    n_data, base_lr, shrink = len(shard), args.lr, 0
-    msg_mb = (eng.plan.factor_bytes_per_worker() + eng.plan.dense_bytes()) / 2 ** 20
-    while eng.step <= args.max_steps:
-        t0 = time.time()
-        x, y = loader.next_batch()
-        stats = eng.train_step(x, y)
-        cur = eng.step - 1
-        if cur % args.log_interval == 0 or cur == args.max_steps:
-            loss, p1, p5 = stats.tolist()
-            dt = time.time() - t0
-            if eng.is_worker:
-                print(worker_line(rank, cur, loader.epochs_completed, (cur * args.batch_size) % n_data, n_data, loss,
-                                  dt, dt, 0.0, 0.0, msg_mb, p1, p5))
-            if eng.is_ps:
-                print(master_line(cur, 0.0, eng.lr, 0.0))
-        if cur % args.eval_freq == 0:
-            if eng.is_ps:
-                eng.save_checkpoint(args.train_dir, cur)
-            if eng.is_worker and rank == first:
-                eng.model.eval()
-                tl, a1, a5, nbt, cnt = 0.0, 0.0, 0.0, 0, 0
-                with torch.no_grad():
-                    for i, (dx, dy) in enumerate(test_loader):
-                        if args.eval_batches and i >= args.eval_batches:
-                            break
-                        dx, dy = dx.to(dev), dy.to(dev)
-                        out = eng.model(dx)
-                        tl += F.cross_entropy(out, dy, reduction="sum").item()
-                        b1, b5 = accuracy(out, dy, (1, 5))
-                        a1 += b1.item(); a5 += b5.item(); nbt += 1; cnt += len(dy)
-                print(test_line(cur, tl / max(cnt, 1), a1 / max(nbt, 1), a5 / max(nbt, 1)))
-                eng.model.train()
-        if eng.step % 50 == 0:  # shrinkage_freq (master:232-234), actually applied here
-            shrink += 1
-            eng.set_lr(base_lr * args.lr_shrinkage ** shrink)
-    err = eng.error_code()
-    if err:
-        print("rank %d: device error code %d" % (rank, err))
-    loader.close()
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    """``--backend p2p`` entry of the launcher (kept here for the old import path)."""
+    from .p2p_launcher import run_p2p_training as _run
+    return _run(args)

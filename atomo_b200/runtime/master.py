@@ -153,6 +153,7 @@ class SyncReplicasMaster_NN(NN_Trainer):
                         self.comm.send_kill(w, self.cur_step)
                 self.comm.drain()
 
+            self._take_aux_buffers(coded_msgs)
             decode_start = time.time()
             n_used = self._decode(coded_msgs)
             decode_dur = time.time() - decode_start
@@ -175,6 +176,16 @@ class SyncReplicasMaster_NN(NN_Trainer):
 
     def async_bcast_layer_weights_bcast(self):
         self.comm.bcast_params(self.flat_params)
+
+    def _take_aux_buffers(self, coded_msgs: dict):
+        """Strip the auxiliary entries workers append to their code lists; BatchNorm running statistics sent by the
+        first worker on checkpoint steps are copied into the PS's network before it is saved."""
+        for w, codes in coded_msgs.items():
+            if codes and isinstance(codes[-1], dict) and codes[-1].get("__aux__") == "buffers":
+                aux = codes.pop()
+                with torch.no_grad():
+                    for b, t in zip(self.network.buffers(), aux["tensors"]):
+                        b.copy_(t.to(b.device, b.dtype))
 
     def _decode(self, coded_msgs: dict) -> int:
         for _, codes in coded_msgs.items():

@@ -230,7 +230,7 @@ class ShadowEngine:
         self.vgrads_mc = h.region_mc_ptr("vgrads")
         sm = torch.cuda.get_device_properties(dev).multi_processor_count
         self.ps_grid = ps_grid or 3 * sm
-        self.tstats = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.tstats = torch.zeros(32, dtype=torch.int64, device=dev)
         self.loss_buf = torch.zeros(3, dtype=torch.float32, device=dev)
         self.static_x = self.static_y = self.graph = None
 
@@ -268,13 +268,24 @@ class ShadowEngine:
         return int(self.ctrl_i32[0].item())
 
     def phase_stats(self, reset: bool = True) -> dict:
+        """Average device-side microseconds per step since the last reset (globaltimer stamps taken inside the
+        kernels, so they are valid under CUDA-graph replay):
+
+        * ``param_wait_us``  blocked at the start of a step until every owner published the parameters,
+        * ``encode_us``      encode + project kernels of all groups (first CTA in -> last CTA out; they overlap with
+                             backward except for the final group),
+        * ``to_push_us``     step start -> this worker's last push flag (forward + backward + its encode tail),
+        * ``to_params_us``   step start -> this owner's parameters published (owners only),
+        * ``ps_wait_push_us`` / ``ps_work_us``  per step, summed over the groups this owner serves."""
         t = self.tstats.tolist()
-        out = {"param_wait_us": t[3] / max(t[4], 1) / 1e3}
+        steps = max(t[4], 1)
+        out = {"param_wait_us": t[3] / steps / 1e3, "encode_us": t[5] / steps / 1e3, "to_push_us": t[8] / steps / 1e3}
         if self.is_owner:
-            out["ps_wait_push_us"] = t[0] / max(t[2], 1) / 1e3     # per PS launch (one per group)
-            out["ps_work_us"] = t[1] / max(t[2], 1) / 1e3
+            out["ps_wait_push_us"] = t[0] / steps / 1e3
+            out["ps_work_us"] = t[1] / steps / 1e3
+            out["to_params_us"] = t[7] / steps / 1e3
         if reset:
-            self.tstats.zero_()
+            self.tstats[:9].zero_()
         return out
 
     # ------------------------------------------------------------------------------------------------------
@@ -303,19 +314,22 @@ class ShadowEngine:
                         self.selcount.data_ptr(), self.sigma.data_ptr(), self.t_arena_peer.data_ptr(), self.n_owners,
                         pl.arena_floats, self.wstage.data_ptr(), self.ctrl.data_ptr(), 0,
                         self.vprev.data_ptr() if self.vprev is not None else 0, self.max_sweeps, self.random_sample,
-                        self.waterfill, self.systematic, self.worker_index, self.resample_empty, self.kflags)
+                        self.waterfill, self.systematic, self.worker_index, self.resample_empty, self.kflags,
+                        self.tstats.data_ptr(), g)
             self._nlaunch += 1
         elif nt > 0:
             # dense code: only the staging copies of the bf16 gradients
             C.v2_encode(self.t_units.data_ptr(), self.t_enc_tiles.data_ptr(), t0, nt, self.t_gptr.data_ptr(),
                         self.gpart.data_ptr(), self.counters.data_ptr(), self.vsel.data_ptr(),
                         self.selcount.data_ptr(), 0, self.t_arena_peer.data_ptr(), self.n_owners, pl.arena_floats,
-                        self.wstage.data_ptr(), self.ctrl.data_ptr(), 0, 0, 0, False, False, False, self.worker_index, False, self.kflags)
+                        self.wstage.data_ptr(), self.ctrl.data_ptr(), 0, 0, 0, False, False, False, self.worker_index, False, self.kflags,
+                        self.tstats.data_ptr(), g)
             self._nlaunch += 1
         C.v2_project(self.t_units.data_ptr(), self.t_enc_tiles.data_ptr(), t0, nt, self.t_gptr.data_ptr(),
                      self.vsel.data_ptr(), self.selcount.data_ptr(), self.t_arena_peer.data_ptr(),
                      self.t_sig_owner.data_ptr(), self.n_owners, pl.arena_floats, self.worker_index, g,
-                     self.ctrl.data_ptr(), self.cnt_enc_group + 4 * g, self.kflags)
+                     self.ctrl.data_ptr(), self.cnt_enc_group + 4 * g, self.kflags, self.tstats.data_ptr(),
+                     self._fired == self.G, nt > 0)
         self._nlaunch += 1
 
     def _launch_ps(self, g: int, final: bool):

@@ -166,6 +166,13 @@ class DistributedWorker(NN_Trainer):
         return msgs, nbytes
 
     def _send_grads(self, msgs):
+        if self.rank == 1 and self._eval_freq and self.cur_step % self._eval_freq == 0:
+            # checkpoint step: the first worker ships its BatchNorm running statistics with the gradients so the
+            # PS's model_step_<N> carries TRAINED buffers (the PS never runs a forward pass; the reference's PS
+            # checkpoints had untrained BN statistics, which is why it kept them off for ResNet, master:228-230)
+            bufs = [b.detach().to("cpu") for b in self.network.buffers()]
+            if bufs:
+                msgs = list(msgs) + [{"__aux__": "buffers", "encode": False, "tensors": bufs}]
         self.comm.push(msgs, self.cur_step)
 
     def _generate_model_path(self):

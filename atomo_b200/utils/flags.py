@@ -57,8 +57,13 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--nesterov", type=bool_flag, default=False)
     p.add_argument("--resume", type=bool_flag, default=False)
     p.add_argument("--dtype", type=str, default="fp32", choices=["fp32", "bf16"])
-    p.add_argument("--ps-mode", type=str, default="colocated", choices=["colocated", "dedicated"],
-                   help="p2p backend: rank 0 hosts the PS and (colocated) also trains")
+    p.add_argument("--ps-mode", type=str, default="sharded", choices=["sharded", "colocated", "dedicated"],
+                   help="p2p backend: sharded = every GPU trains and owns 1/N of the PS tiles (bf16 engine); "
+                        "colocated = rank 0 hosts the whole PS and also trains; dedicated = rank 0 only serves")
+    p.add_argument("--groups", type=int, default=5, help="p2p/bf16: backward groups pushed while backward runs")
+    p.add_argument("--shrinkage-freq", type=int, default=50, help="steps between LR shrinkages (reference: 50)")
+    p.add_argument("--flag-timeout", type=float, default=120.0,
+                   help="p2p: seconds a device-side wait on a peer flag may spin before the sticky error code is set")
     p.add_argument("--straggler-kill", type=bool_flag, default=False,
                    help="with --num-aggregate < workers: layer-wise (split) backward on the workers and a tag-77 kill "
                         "signal from the PS once enough gradients arrived (LeNet / FC / ResNet18 / ResNet34)")

@@ -32,7 +32,7 @@ for shape in [(64, 64, 3, 3), (128, 64, 1, 1), (512, 512, 3, 3), (48, 16, 5, 5)]
             h.C.v2_encode(h.t_units.data_ptr(), h.t_enc.data_ptr(), t0, nt, gptr.data_ptr(), h.gpart.data_ptr(),
                           h.counters.data_ptr(), h.vsel.data_ptr(), h.selcount.data_ptr(), h.sigma.data_ptr(),
                           h.t_arena_peer.data_ptr(), 1, pl.arena_floats, h.stage[0].data_ptr(), h.ctrl.data_ptr(), 0,
-                          h.vprev.data_ptr() if h.vprev is not None else 0, h.max_sweeps, True, False, False, 0, False, 0)
+                          h.vprev.data_ptr() if h.vprev is not None else 0, h.max_sweeps, True, False, False, 0, False, 0, 0, 0)
         us = timed(enc)
         print("%-18s units %d cols %s tiles %3d  warm=%-5s sweeps<=%-2d  encode launch %.1f us" %
               (shape, pl.n_coded, [u.cols for u in pl.units if u.coded][:1], nt, warm, sw, us))

@@ -54,7 +54,7 @@ class H2:
         self.t_vparams_peer = i64([self.vparams.data_ptr()])
         self.t_vgrads_peer = i64([t.data_ptr() for t in self.vgrads])
         self.t_stage_peer = i64([t.data_ptr() for t in self.stage])
-        self.tstats = z(8, torch.int64)
+        self.tstats = z(32, torch.int64)
         self.max_sweeps = max_sweeps
         self.vprev = None
         if warm:
@@ -100,10 +100,11 @@ class H2:
                         self.t_arena_peer.data_ptr(), 1, pl.arena_floats, self.stage[w].data_ptr(), self.ctrl.data_ptr(),
                         uniforms.data_ptr() if uniforms is not None else 0,
                         self.vprev.data_ptr() if self.vprev is not None else 0, self.max_sweeps, random_sample,
-                        waterfill, systematic, w, False, 0)
+                        waterfill, systematic, w, False, 0, 0, g)
             C.v2_project(self.t_units.data_ptr(), self.t_enc.data_ptr(), t0, nt, gptr.data_ptr(), self.vsel.data_ptr(),
                          self.selcount.data_ptr(), self.t_arena_peer.data_ptr(), self.t_sig_peer.data_ptr(), 1,
-                         pl.arena_floats, w, g, self.ctrl.data_ptr(), self.counters.data_ptr() + 4 * (pl.n_coded + g), 0)
+                         pl.arena_floats, w, g, self.ctrl.data_ptr(), self.counters.data_ptr() + 4 * (pl.n_coded + g), 0, 0,
+                         False, False)
         torch.cuda.synchronize()
 
     def ps(self, grid=64):

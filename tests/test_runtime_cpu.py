@@ -194,3 +194,16 @@ def test_kill_signal_is_step_stamped():
     assert not t.kill_requested(3)
     t.send_kill(2, 7)
     assert not t.kill_requested(8) and t.kill_requested(7)   # a step-7 signal cannot abort step 8
+
+
+def test_ps_checkpoint_of_a_bn_network_carries_trained_statistics(tmp_path):
+    """the PS never runs a forward pass, so its own BatchNorm buffers stay at (0, 1).  The first worker
+    ships its running statistics with the gradients of every checkpoint step; the saved model_step_<N> must
+    therefore hold trained buffers (the evaluator loads it under .eval())."""
+    d = str(tmp_path) + "/"
+    _run_launcher(["--nproc", "2", "--network", "ResNet18", "--dataset", "Cifar10", "--code", "sgd", "--batch-size", "8",
+                   "--max-steps", "2", "--eval-freq", "2", "--train-dir", d, "--master-port", "29597"], timeout=400)
+    sd = torch.load(d + "model_step_2", weights_only=False)
+    assert float(sd["bn1.running_mean"].abs().sum()) > 0
+    assert not torch.allclose(sd["bn1.running_var"], torch.ones_like(sd["bn1.running_var"]))
+    assert int(sd["bn1.num_batches_tracked"]) >= 2
