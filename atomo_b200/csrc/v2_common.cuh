@@ -32,7 +32,7 @@ struct Unit2 {
   int own0;             // owner of PS tile 0 (tile j -> (own0 + j) % n_owners)
   int ps_tile0, n_ps;
   int ts_index;         // index among coded units (vsel / selcount / counters)
-  int pad;
+  int ubits;            // 0: U fp32 [rows][rcap]; 8 (QSVD): U int8 [rows][rcap] + one fp32 scale per row
 };
 static_assert(sizeof(Unit2) == 112, "Unit2 layout must match ops/plan2.py UNIT_FMT");
 
@@ -139,6 +139,10 @@ __device__ __forceinline__ void load_slab_tile_ldg(const __nv_bfloat16* gbase, i
 __host__ __device__ inline long long slot2_u_off(int rcap, int cols) {
   long long o = 4 + (long long)rcap + (long long)rcap * cols;
   return (o + 3) & ~3LL;
+}
+// QSVD slots: int8 U occupies rows*rcap/4 floats (rounded to 4), then rows fp32 scales (max |u| of the row)
+__host__ __device__ inline long long slot2_scale_off(int rows, int rcap, int cols) {
+  return slot2_u_off(rcap, cols) + (((long long)rows * rcap / 4 + 3) & ~3LL);
 }
 
 }  // namespace v2

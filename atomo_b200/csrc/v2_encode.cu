@@ -571,6 +571,21 @@ struct ProjArgs {
 
 constexpr int PROJ_SMEM = ENC_HDR + ENC_TILE_BYTES + V2_MAX_COLS * V2_RCAP_MAX * 4;
 
+// QSVD: quantize one float4 of a U row to 4 x int8 with unbiased stochastic rounding against the row scale
+__device__ __forceinline__ int quant4_i8(const float4 v, float inv_scale127, const uint32_t (&rnd)[4]) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  int packed = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float t = x[j] * inv_scale127;                       // in [-127, 127]
+    const float fl = floorf(t);
+    int q = (int)fl + ((Philox::to_uniform(rnd[j]) < (t - fl)) ? 1 : 0);
+    q = max(-127, min(127, q));
+    packed |= (q & 0xff) << (8 * j);
+  }
+  return packed;
+}
+
 __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs a) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(enc_smem);
   uint32_t* tile = reinterpret_cast<uint32_t*>(enc_smem + ENC_HDR);
@@ -604,6 +619,8 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs 
         const int owner = (u.own0 + (int)(r / u.ps_rows)) % a.n_owners;
         float4* dst = reinterpret_cast<float4*>(a.arena_peer[owner] + uoff + r * rcap);
         const uint32_t* col = tile + (size_t)(s * K) * pitch + ri;
+        float rowmax = 0.f;          // QSVD: first pass finds max |u| of the row, second pass quantizes
+        for (int pass = (u.ubits == 8 ? 0 : 1); pass < 2; ++pass)
         for (int g0 = 0; g0 < c4; g0 += 2) {
           float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
           const bool two = (g0 + 1) < c4;
@@ -625,8 +642,27 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs 
               a1.z = fmaf(x1, w1.z, a1.z); a1.w = fmaf(x1, w1.w, a1.w);
             }
           }
-          st_na_f4(dst + g0, a0);
-          if (two) st_na_f4(dst + g0 + 1, a1);
+          if (u.ubits != 8) {
+            st_na_f4(dst + g0, a0);
+            if (two) st_na_f4(dst + g0 + 1, a1);
+          } else if (pass == 0) {
+            rowmax = fmaxf(rowmax, fmaxf(fmaxf(fabsf(a0.x), fabsf(a0.y)), fmaxf(fabsf(a0.z), fabsf(a0.w))));
+            if (two) rowmax = fmaxf(rowmax, fmaxf(fmaxf(fabsf(a1.x), fabsf(a1.y)), fmaxf(fabsf(a1.z), fabsf(a1.w))));
+          } else {
+            float* sbase = a.arena_peer[owner] + (long long)a.worker * a.arena_floats + u.slot_off;
+            int* q8 = reinterpret_cast<int*>(sbase + slot2_u_off(rcap, n)) + (r * rcap >> 2);
+            const float inv = rowmax > 0.f ? 127.f / rowmax : 0.f;
+            uint32_t rnd[4];
+            Philox::gen(a.ctrl->seed ^ 0x51ed270b1ULL, (uint32_t)r, (uint32_t)g0, (uint32_t)t.unit,
+                        ((uint32_t)a.worker << 24) ^ (uint32_t)a.ctrl->step, rnd);
+            q8[g0] = quant4_i8(a0, inv, rnd);
+            if (two) {
+              Philox::gen(a.ctrl->seed ^ 0x51ed270b1ULL, (uint32_t)r, (uint32_t)(g0 + 1), (uint32_t)t.unit,
+                          ((uint32_t)a.worker << 24) ^ (uint32_t)a.ctrl->step, rnd);
+              q8[g0 + 1] = quant4_i8(a1, inv, rnd);
+            }
+            if (g0 == 0) sbase[slot2_scale_off(u.rows, rcap, n) + r] = rowmax;
+          }
         }
       }
     } else {
@@ -635,6 +671,8 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs 
         const int owner = (u.own0 + (int)(r / u.ps_rows)) % a.n_owners;
         float4* dst = reinterpret_cast<float4*>(a.arena_peer[owner] + uoff + r * rcap);
         const __nv_bfloat16* row = gb + r * u.rs;
+        float rowmax = 0.f;
+        for (int pass = (u.ubits == 8 ? 0 : 1); pass < 2; ++pass)
         for (int g0 = 0; g0 < c4; g0 += 2) {
           float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
           const bool two = (g0 + 1) < c4;
@@ -649,8 +687,27 @@ __global__ void __launch_bounds__(ENC_THREADS) v2_project_kernel(const ProjArgs 
               a1.z = fmaf(x, v1.z, a1.z); a1.w = fmaf(x, v1.w, a1.w);
             }
           }
-          st_na_f4(dst + g0, a0);
-          if (two) st_na_f4(dst + g0 + 1, a1);
+          if (u.ubits != 8) {
+            st_na_f4(dst + g0, a0);
+            if (two) st_na_f4(dst + g0 + 1, a1);
+          } else if (pass == 0) {
+            rowmax = fmaxf(rowmax, fmaxf(fmaxf(fabsf(a0.x), fabsf(a0.y)), fmaxf(fabsf(a0.z), fabsf(a0.w))));
+            if (two) rowmax = fmaxf(rowmax, fmaxf(fmaxf(fabsf(a1.x), fabsf(a1.y)), fmaxf(fabsf(a1.z), fabsf(a1.w))));
+          } else {
+            float* sbase = a.arena_peer[owner] + (long long)a.worker * a.arena_floats + u.slot_off;
+            int* q8 = reinterpret_cast<int*>(sbase + slot2_u_off(rcap, n)) + (r * rcap >> 2);
+            const float inv = rowmax > 0.f ? 127.f / rowmax : 0.f;
+            uint32_t rnd[4];
+            Philox::gen(a.ctrl->seed ^ 0x51ed270b1ULL, (uint32_t)r, (uint32_t)g0, (uint32_t)t.unit,
+                        ((uint32_t)a.worker << 24) ^ (uint32_t)a.ctrl->step, rnd);
+            q8[g0] = quant4_i8(a0, inv, rnd);
+            if (two) {
+              Philox::gen(a.ctrl->seed ^ 0x51ed270b1ULL, (uint32_t)r, (uint32_t)(g0 + 1), (uint32_t)t.unit,
+                          ((uint32_t)a.worker << 24) ^ (uint32_t)a.ctrl->step, rnd);
+              q8[g0 + 1] = quant4_i8(a1, inv, rnd);
+            }
+            if (g0 == 0) sbase[slot2_scale_off(u.rows, rcap, n) + r] = rowmax;
+          }
         }
       }
     }

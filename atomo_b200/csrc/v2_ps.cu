@@ -158,20 +158,60 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
   Ctrl2* ctrl = a.ctrl;
   const int step = ctrl->step;
 
-  // ---- 1. wait for the W pushes of this group ------------------------------------------------------------
+  // ---- 1. wait for the pushes of this group ------------------------------------------------------------
+  // Default: all W workers.  With Ctrl2::num_aggregate = N < W (the reference's --num-aggregate, parsed at
+  // distributed_nn.py:67 and never used there) the owner proceeds as soon as N pushes of THIS step have landed:
+  // CTA 0 decides the set once and publishes it (mask, then a step stamp) so that every CTA of the launch
+  // averages the same workers; late pushes carry an older step in their flag and are simply never counted.
+  __shared__ unsigned int s_mask;
   long long t_enter = 0, t_ready = 0;
   if (tid == 0) {
     t_enter = globaltimer_ns();
     bool ok = true;
     const int* flags = a.sig + SIG_PUSH + a.group * MAX_WORKERS;
-    for (int w = 0; w < a.W; ++w) ok = spin_wait_ge(flags + w, step, a.timeout) && ok;
+    const int need = (ctrl->num_aggregate > 0 && ctrl->num_aggregate < a.W) ? ctrl->num_aggregate : a.W;
+    unsigned int mask = a.W >= 32 ? 0xffffffffu : ((1u << a.W) - 1u);
+    if (need == a.W) {
+      for (int w = 0; w < a.W; ++w) ok = spin_wait_ge(flags + w, step, a.timeout) && ok;
+    } else {
+      int* mslot = a.sig + SIG_MASK + 2 * a.group;
+      if (blockIdx.x == 0) {
+        const long long t0 = clock64();
+        int backoff = 32;
+        for (;;) {
+          mask = 0;
+          int n = 0;
+          for (int w = 0; w < a.W; ++w)
+            if (ld_acquire_sys(flags + w) >= step) { mask |= 1u << w; ++n; }
+          if (n >= need) break;
+          __nanosleep(backoff);
+          if (backoff < 1024) backoff <<= 1;
+          if (clock64() - t0 > a.timeout) { ok = false; break; }
+        }
+        mslot[0] = (int)mask;
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(mslot + 1), "r"(ok ? step : -step) : "memory");
+      } else {
+        int v;
+        const long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(mslot + 1) : "memory");
+          if (clock64() - t0 > 2 * a.timeout) { v = -step; break; }
+        } while (v != step && v != -step);
+        ok = v == step;
+        mask = (unsigned int)ld_cg_i(mslot);
+      }
+    }
     if (!ok) atomicOr(&ctrl->error, ERR2_WAIT_PUSH);
     s_ok = ok ? 1 : 0;
     s_bad = 0;
+    s_mask = mask;
     t_ready = globaltimer_ns();
   }
   __syncthreads();
   const bool ok = s_ok != 0;
+  const unsigned int wmask = s_mask;
+  const bool all_workers = wmask == (a.W >= 32 ? 0xffffffffu : ((1u << a.W) - 1u));
 
   OptC c;
   c.lr = ctrl->lr; c.mu = ctrl->momentum; c.damp = ctrl->dampening; c.wd = ctrl->weight_decay;
@@ -182,7 +222,7 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
     c.bc1 = 1.f - powf(c.b1, t);
     c.sbc2 = sqrtf(1.f - powf(c.b2, t));
   }
-  const float inv_w = a.inv_w;
+  const float inv_w = all_workers ? a.inv_w : 1.f / (float)max(__popc(wmask), 1);
 
   const int per_cta = (a.ntiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * per_cta;
@@ -198,11 +238,12 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
       for (int v = tid; v < nvec; v += blockDim.x) {
         const long long e = e0 + 4LL * v;
         float4 g;
-        if (a.vgrads_mc != nullptr) {
+        if (a.vgrads_mc != nullptr && all_workers) {
           g = multimem_ld_reduce_f4(reinterpret_cast<const float4*>(a.vgrads_mc + e));
         } else {
           g = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int w = 0; w < a.W; ++w) {
+            if (!((wmask >> w) & 1u)) continue;
             const float4 x = ld_cg_f4(reinterpret_cast<const float4*>(a.vgrads_peer[w] + e));
             g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
           }
@@ -232,7 +273,8 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
       for (int i = (nvec << 2) + tid; i < t.b; i += blockDim.x) {
         const long long e = e0 + i;
         float g = 0.f;
-        for (int w = 0; w < a.W; ++w) g += ld_cg_f(a.vgrads_peer[w] + e);
+        for (int w = 0; w < a.W; ++w)
+          if ((wmask >> w) & 1u) g += ld_cg_f(a.vgrads_peer[w] + e);
         float p = a.vparams_local[e], m = a.vmom[e], q = 0.f, qm = 0.f;
         if (c.opt != OPT_SGD) { q = a.vsq[e]; if (c.opt == OPT_AMSGRAD) qm = a.vsqmax[e]; }
         opt_update(g * inv_w, p, m, q, qm, c);
@@ -254,6 +296,7 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = 0.f;
         for (int w = 0; w < a.W; ++w) {
+          if (!((wmask >> w) & 1u)) continue;
           const uint4 y = ld_cg_u4(a.stage_peer[w] + s0 + 8LL * v);
           const uint32_t ws[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -266,7 +309,7 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
       for (int i = (nvec << 3) + tid; i < t.b; i += blockDim.x) {
         float g = 0.f;
         for (int w = 0; w < a.W; ++w)
-          g += ld_cg_bf16(a.stage_peer[w] + s0 + i);
+          if ((wmask >> w) & 1u) g += ld_cg_bf16(a.stage_peer[w] + s0 + i);
         update1(a, c, e0 + i, g * inv_w);
       }
       continue;
@@ -279,8 +322,11 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
     __syncthreads();   // previous tile is done with shared memory
     if (tid < a.W) {
       const int* hdr = reinterpret_cast<const int*>(a.arenas + (long long)tid * a.arena_floats + u.slot_off);
-      int cc = ld_cg_i(hdr);
-      if (ld_cg_i(hdr + 1) != step) { cc = 0; s_bad = 1; }   // stale slot: a push of another step
+      int cc = 0;
+      if ((wmask >> tid) & 1u) {
+        cc = ld_cg_i(hdr);
+        if (ld_cg_i(hdr + 1) != step) { cc = 0; s_bad = 1; }   // stale slot: a push of another step
+      }
       cnt[tid] = min(max(cc, 0), rcap);
     }
     __syncthreads();
@@ -320,9 +366,18 @@ __global__ void __launch_bounds__(PS2_THREADS) v2_ps_kernel(const PsArgs2 a) {
         const int w = grp_w[g], a0 = grp_a0[g];
         const int kbase = koff[w] + a0 - k0;
         if (kbase >= kc || kbase + 4 <= 0) continue;
-        const float* U = a.arenas + (long long)w * a.arena_floats + u.slot_off + slot2_u_off(rcap, n);
-        const float4 u4 = ld_cg_f4(reinterpret_cast<const float4*>(U + (long long)(row0 + r) * rcap + a0));
-        const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
+        const float* slotw = a.arenas + (long long)w * a.arena_floats + u.slot_off;
+        const float* U = slotw + slot2_u_off(rcap, n);
+        float uv[4];
+        if (u.ubits == 8) {   // QSVD: 4 x int8 and the row scale
+          const int q = ld_cg_i(reinterpret_cast<const int*>(U) + (((long long)(row0 + r) * rcap + a0) >> 2));
+          const float sc = ld_cg_f(slotw + slot2_scale_off(u.rows, rcap, n) + row0 + r) * (1.f / 127.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uv[j] = (float)(signed char)((q >> (8 * j)) & 0xff) * sc;
+        } else {
+          const float4 u4 = ld_cg_f4(reinterpret_cast<const float4*>(U + (long long)(row0 + r) * rcap + a0));
+          uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
+        }
         const int lim = cnt[w] - a0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -430,6 +485,13 @@ __global__ void v2_wait_params_kernel(const int* sig, int n_owners, Ctrl2* ctrl,
     if (!spin_wait_ge(sig + SIG_PARAM + threadIdx.x, ctrl->step, timeout)) atomicOr(&ctrl->error, ERR2_WAIT_PARAM);
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // a straggler that was left out of an aggregation (num_aggregate < W) finds the owners already further along:
+    // it skips ahead to the step whose parameters are in place instead of pushing gradients nobody waits for
+    int m = 0x7fffffff;
+    for (int o = 0; o < n_owners; ++o) m = min(m, ld_acquire_sys(sig + SIG_PARAM + o));
+    if (m != 0x7fffffff && m > ctrl->step) ctrl->step = m;
+  }
   if (threadIdx.x == 0 && tstats != nullptr) {
     const long long now = globaltimer_ns();
     tstats[3] += now - t0; tstats[4] += 1;

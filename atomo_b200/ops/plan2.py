@@ -60,8 +60,17 @@ def slot_u_off(rcap: int, cols: int) -> int:
     return _round_up(4 + rcap + rcap * cols, 4)
 
 
-def slot_floats(rows: int, cols: int, rcap: int) -> int:
+def slot_floats(rows: int, cols: int, rcap: int, ubits: int = 0) -> int:
+    """Slot size in floats.  ``ubits == 8`` (QSVD): U is stored as int8 [rows][rcap] followed by one fp32 scale per
+    row instead of fp32 [rows][rcap]."""
+    if ubits == 8:
+        return _round_up(slot_u_off(rcap, cols) + _round_up(rows * rcap // 4, 4) + rows, 32)
     return _round_up(slot_u_off(rcap, cols) + rows * rcap, 32)
+
+
+def slot_scale_off(rows: int, cols: int, rcap: int) -> int:
+    """Float offset (inside the slot) of the per-row scales of an int8 U."""
+    return slot_u_off(rcap, cols) + _round_up(rows * rcap // 4, 4)
 
 
 def slot_capacity(cols: int, rank: int, systematic: bool) -> int:
@@ -125,13 +134,14 @@ class Unit2:
     ps_tile0: int = 0
     n_ps: int = 0
     ts_index: int = -1      # index among coded units (vsel / selcount / counters)
+    ubits: int = 0          # 0: U stored fp32; 8: QSVD, U stochastically rounded to int8 with a per-row scale
 
     def pack(self) -> bytes:
         return struct.pack(UNIT_FMT, self.w_off, self.g_off, self.slot_off, self.gpart_off, self.kind, self.pidx,
                            self.rows, self.cols, self.K, self.I, self.rs, self.cs, self.rcap,
                            struct.unpack("<i", struct.pack("<f", self.budget))[0], self.numel, self.group,
                            self.enc_tile0, self.n_enc, self.ps_rows, self.own0, self.ps_tile0, self.n_ps,
-                           self.ts_index, 0)
+                           self.ts_index, self.ubits)
 
     @property
     def coded(self) -> bool:
@@ -167,7 +177,8 @@ class Plan2:
         return b"".join(struct.pack(TILE_FMT, *t) for t in tiles) or b"\0" * TILE_BYTES
 
     def factor_bytes_per_worker(self) -> int:
-        return sum(4 * (4 + u.rcap + u.rcap * u.cols + u.rows * u.rcap) for u in self.units if u.coded)
+        return sum(4 * (4 + u.rcap + u.rcap * u.cols) + (u.rows * (u.rcap + 4) if u.ubits == 8 else 4 * u.rows * u.rcap)
+                   for u in self.units if u.coded)
 
     def expected_factor_bytes(self) -> float:
         """Bytes actually stored per worker and step for the expected number of atoms (U is written in groups
@@ -176,7 +187,8 @@ class Plan2:
         for u in self.units:
             if u.coded:
                 atoms = min(u.budget if u.budget > 0 else u.cols, u.cols)
-                tot += 4 * (4 + u.rcap + u.rcap * u.cols) + 4 * u.rows * min(u.rcap, _round_up(int(atoms + 0.999), 4))
+                a4 = min(u.rcap, _round_up(int(atoms + 0.999), 4))
+                tot += 4 * (4 + u.rcap + u.rcap * u.cols) + (u.rows * (a4 + 4) if u.ubits == 8 else 4 * u.rows * a4)
         return tot
 
     def dense_bytes(self) -> int:
@@ -228,6 +240,9 @@ def build_plan2(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 
                 n_owners: int = 1, n_groups: int = 4, groups: Optional[Sequence[int]] = None,
                 block_cols: int = BLOCK_COLS, min_coded_numel: int = 256) -> Plan2:
     shapes = [tuple(int(d) for d in s) for s in shapes]
+    ubits = 0
+    if code == "qsvd":          # QSVD: spectral atoms with quantized left factors (README.md:141-142 of the reference)
+        code, ubits = "svd", 8
     if groups is None:
         groups = default_groups(shapes, n_groups)
     n_groups = max(groups) + 1 if groups else 1
@@ -326,8 +341,9 @@ def build_plan2(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 
             if u.coded:
                 u.ts_index = n_coded
                 n_coded += 1
+                u.ubits = ubits
                 u.slot_off = slot_off
-                slot_off += slot_floats(u.rows, u.cols, u.rcap)
+                slot_off += slot_floats(u.rows, u.cols, u.rcap, ubits)
                 u.gpart_off = gpart_off
                 gpart_off += u.n_enc * u.cols * u.cols
                 u.ps_tile0 = len(ps_by_group[g])

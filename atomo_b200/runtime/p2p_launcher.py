@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 
 def _build_engine(args, model, rank, world):
-    shadow = args.dtype == "bf16" and args.code.lower() in ("svd", "sgd", "dense", "lossless")
+    shadow = args.dtype == "bf16" and args.code.lower() in ("svd", "qsvd", "sgd", "dense", "lossless")
     if shadow:
         from .shadow_engine import ShadowEngine
         return ShadowEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr,

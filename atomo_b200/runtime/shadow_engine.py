@@ -64,8 +64,8 @@ class ShadowEngine:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         dev = self.device
         self.code = {"dense": "sgd", "lossless": "sgd"}.get(code.lower(), code.lower())
-        if self.code not in ("svd", "sgd"):
-            raise ValueError("ShadowEngine codes: svd | sgd (qsgd / terngrad / entrywise run on FusedEngine)")
+        if self.code not in ("svd", "sgd", "qsvd"):
+            raise ValueError("ShadowEngine codes: svd | qsvd | sgd (qsgd / terngrad / entrywise run on FusedEngine)")
         self.svd_rank = int(svd_rank)
         if world == 1:
             ps_mode = "colocated"
@@ -308,7 +308,7 @@ class ShadowEngine:
             lo, hi = self.w_range[g]
             if hi > lo:   # pageable source: staged synchronously, safe against the host table changing next step
                 self.t_gptr[lo:hi].copy_(torch.from_numpy(self.host_gptr[lo:hi].copy()))
-        if nt > 0 and self.code == "svd":
+        if nt > 0 and self.code in ("svd", "qsvd"):
             C.v2_encode(self.t_units.data_ptr(), self.t_enc_tiles.data_ptr(), t0, nt, self.t_gptr.data_ptr(),
                         self.gpart.data_ptr(), self.counters.data_ptr(), self.vsel.data_ptr(),
                         self.selcount.data_ptr(), self.sigma.data_ptr(), self.t_arena_peer.data_ptr(), self.n_owners,

@@ -168,7 +168,7 @@ def main():
     model = build_model(args.network, ncls, args.dataset)
     engine = args.engine
     if engine == "auto":
-        engine = "shadow" if (args.dtype == "bf16" and args.code in ("svd", "sgd") and args.channels_last) else "fused"
+        engine = "shadow" if (args.dtype == "bf16" and args.code in ("svd", "qsvd", "sgd") and args.channels_last) else "fused"
     if engine == "shadow":
         from atomo_b200.runtime.shadow_engine import ShadowEngine
         eng = ShadowEngine(model, rank, world, code=args.code, svd_rank=args.svd_rank, lr=args.lr,

@@ -141,7 +141,12 @@ class H2:
         s = base[4:4 + u.rcap][:count]
         V = base[4 + u.rcap:4 + u.rcap + u.rcap * u.cols].view(u.rcap, u.cols)[:count]
         uo = self.P.slot_u_off(u.rcap, u.cols)
-        U = base[uo:uo + u.rows * u.rcap].view(u.rows, u.rcap)[:, :count]
+        if u.ubits == 8:      # QSVD: int8 U with one fp32 scale per row
+            q = base[uo:uo + u.rows * u.rcap // 4].view(torch.int8).view(u.rows, u.rcap)[:, :count].float()
+            so = self.P.slot_scale_off(u.rows, u.cols, u.rcap)
+            U = q * (base[so:so + u.rows] / 127.0).unsqueeze(1)
+        else:
+            U = base[uo:uo + u.rows * u.rcap].view(u.rows, u.rcap)[:, :count]
         return count, s, V, U, int(hdr[1])
 
     def write_unit(self, u, flat, mat):
@@ -324,6 +329,108 @@ def test_v2_ps_matches_reference(W, momentum, nesterov, wd, opt):
         assert torch.allclose(h.vparams[vused], rv[vused], **tol)
         if opt == 0 and momentum:
             assert torch.allclose(h.mom[used], rm[used], rtol=3e-4, atol=3e-5)
+
+
+def test_v2_qsvd_quantized_factors_are_unbiased_and_applied_by_the_ps():
+    """--code qsvd on the GPU path: spectral atoms whose left factors travel as int8 with a per-row scale
+    (stochastic rounding).  Same atoms as --code svd for the same seed; |U_q - U| <= scale/127; the mean over many
+    rounding draws converges to U; the PS applies exactly the de-quantized factors."""
+    shapes = [(64, 32, 3, 3), (128, 64, 1, 1), (64,), (10, 512)]
+    lr = 0.1
+    hq, hf = H2(shapes, code="qsvd", rank=3, lr=lr), H2(shapes, code="svd", rank=3, lr=lr)
+    assert hq.plan.arena_floats < 0.6 * hf.plan.arena_floats
+    lq, lf = hq.fill(0, 5), hf.fill(0, 5)
+    hq.encode(0); hf.encode(0)
+    for uq, uf in zip(hq.plan.units, hf.plan.units):
+        if not uq.coded:
+            continue
+        assert uq.ubits == 8 and uf.ubits == 0
+        cq, sq, Vq, Uq, _ = hq.slot(uq, 0)
+        cf, sf, Vf, Uf, _ = hf.slot(uf, 0)
+        assert cq == cf and torch.allclose(sq, sf, rtol=1e-4) and torch.allclose(Vq, Vf, rtol=1e-3, atol=1e-5)
+        if cq:
+            step = Uf.abs().amax(dim=1, keepdim=True) / 127.0
+            assert bool(((Uq - Uf).abs() <= step * 1.001 + 2e-5).all())
+    # unbiased rounding: average the de-quantized U over many draws (the step enters the Philox counter of the
+    # rounding only through the same atoms when sampling is deterministic)
+    ht = H2(shapes, code="qsvd", rank=3)
+    ht.fill(0, 5)
+    acc, T = {}, 200
+    ref = {}
+    hr = H2(shapes, code="svd", rank=3)
+    hr.fill(0, 5)
+    hr.encode(0, random_sample=False)
+    for u in hr.plan.units:
+        if u.coded:
+            ref[u.index] = hr.slot(u, 0)[3].clone()
+    for t in range(T):
+        ht.ctrl.view(torch.int32)[0] = t + 1
+        ht.encode(0, random_sample=False)
+        for u in ht.plan.units:
+            if u.coded:
+                acc[u.index] = acc.get(u.index, 0) + ht.slot(u, 0)[3]
+    for u in ht.plan.units:
+        if u.coded:
+            err = float((acc[u.index] / T - ref[u.index]).abs().max() / ref[u.index].abs().max())
+            assert err < 2.5e-3, (u.kind, err)          # one rounding step is 1/127 = 7.9e-3 of the row maximum
+    # PS applies the de-quantized factors
+    pl = hq.plan
+    est = torch.zeros(pl.w_total, device=hq.dev)
+    for u in pl.units:
+        q = pl.params[u.param]
+        if u.coded:
+            c, s_, V, U, _ = hq.slot(u, 0)
+            if u.kind == hq.P.KIND_SLAB:
+                hq.write_unit(u, est, (U * s_) @ V)
+            else:
+                torch.as_strided(est, (u.rows, u.cols), (u.rs, u.cs), u.w_off).copy_((U * s_) @ V)
+    p0 = hq.master.clone()
+    hq.ps()
+    assert int(hq.ctrl.view(torch.int32)[1]) == 0
+    for q in pl.params:
+        if q.is_w and any(u.coded and u.param == q.index for u in pl.units):
+            sl = slice(q.off, q.off + q.numel)
+            assert torch.allclose(hq.master[sl], (p0 - lr * est)[sl], rtol=3e-4, atol=3e-5)
+
+
+def test_v2_ps_num_aggregate_uses_only_the_workers_that_pushed():
+    """--num-aggregate 2 of 3 workers (backup-worker semantics, the reference's unused flag): worker 1 never
+    pushes this step; the PS must proceed with workers {0, 2}, average over 2, and ignore worker 1's stale slot."""
+    lr = 0.1
+    h = H2(SHAPES, rank=3, W=3, lr=lr)
+    h.ctrl.copy_(torch.frombuffer(bytearray(h.P.pack_ctrl2(step=1, lr=lr, seed=7, num_aggregate=2)), dtype=torch.uint8).to(h.dev))
+    pl = h.plan
+    est_w = torch.zeros(pl.w_total, device=h.dev)
+    est_v = torch.zeros(pl.v_total, device=h.dev)
+    for w in (0, 2):
+        logical = h.fill(w, 40 + w)
+        h.encode(w)
+        tmp = torch.zeros(pl.w_total, device=h.dev)
+        for u in pl.units:
+            q = pl.params[u.param]
+            if u.coded:
+                c, s, V, U, st = h.slot(u, w)
+                if u.kind == h.P.KIND_SLAB:
+                    h.write_unit(u, tmp, (U * s) @ V)
+                else:
+                    torch.as_strided(tmp, (u.rows, u.cols), (u.rs, u.cs), u.w_off).copy_((U * s) @ V)
+            elif u.kind == h.P.KIND_DENSE16:
+                t = logical[q.index]
+                tmp[u.w_off:u.w_off + u.numel] = t.permute(0, 2, 3, 1).reshape(-1) if t.dim() == 4 else t.reshape(-1)
+        est_w += tmp
+        est_v += h.vgrads[w]
+    h.vgrads[1].fill_(1e6)                      # garbage a skipped worker may hold
+    assert int(h.signals[0]) == 1 and int(h.signals[1]) == 0 and int(h.signals[2]) == 1
+    p0, v0 = h.master.clone(), h.vparams.clone()
+    h.ps()
+    assert int(h.ctrl.view(torch.int32)[1]) == 0 and int(h.signals[256]) == 2
+    assert int(h.signals[320]) == 0b101 and int(h.signals[321]) == 1     # published aggregation mask, step stamp
+    used = torch.zeros(pl.w_total, dtype=torch.bool, device=h.dev)
+    vused = torch.zeros(pl.v_total, dtype=torch.bool, device=h.dev)
+    for q in pl.params:
+        (used if q.is_w else vused)[q.off:q.off + q.numel] = True
+    assert torch.allclose(h.master[used], (p0 - lr * est_w / 2)[used], rtol=3e-4, atol=3e-5)
+    assert torch.allclose(h.vparams[vused], (v0 - lr * est_v / 2)[vused], rtol=3e-4, atol=3e-5)
 
 
 def _batch(net, n=32, seed=0):
