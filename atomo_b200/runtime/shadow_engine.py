@@ -55,7 +55,7 @@ class ShadowEngine:
                  group=None, multicast: bool = True, heap_mode: str = "auto", timeout_s: float = 30.0,
                  criterion: Optional[nn.Module] = None, device: Optional[torch.device] = None,
                  ps_grid: int = 0, overlap: bool = True, fused_bn: bool = True, num_aggregate: int = 0,
-                 warm_start: bool = True, max_sweeps: int = 1, main_priority: int = 0,
+                 warm_start: bool = True, max_sweeps: int = 1, main_priority: int = 0, debug_jitter_us: float = 0.0,
                  side_priority: int = -1, resample_empty: bool = False):
         self.C = load_ext()
         C = self.C
@@ -91,6 +91,9 @@ class ShadowEngine:
         self.random_sample = random_sample
         self.resample_empty = resample_empty
         self.kflags = 1 if os.environ.get("ATOMO_NO_TMA") else 0     # bit 0: plain loads instead of TMA bulk copies
+        # protocol fuzzing (tests): random device-side delays before every push / PS launch, different on every rank
+        self._jitter_us = float(debug_jitter_us)
+        self._jitter_rng = np.random.default_rng(1234 + rank)
         self.use_graph, self.overlap = use_graph, overlap
         self.criterion = criterion or nn.CrossEntropyLoss()
         self.timeout_ticks = int(timeout_s * 1.5e9)
@@ -359,6 +362,8 @@ class ShadowEngine:
         self.ev_ready[g].record(cur)
         self.s_enc.wait_event(self.ev_ready[g])
         with torch.cuda.stream(self.s_enc):
+            if self._jitter_us:
+                torch.cuda._sleep(int(self._jitter_rng.uniform(0, self._jitter_us) * 1900))
             self._launch_encode(g)
             self.ev_push[g].record(self.s_enc)
             if final:
@@ -366,6 +371,8 @@ class ShadowEngine:
         if self.is_owner:
             self.s_ps.wait_event(self.ev_push[g])
             with torch.cuda.stream(self.s_ps):
+                if self._jitter_us:
+                    torch.cuda._sleep(int(self._jitter_rng.uniform(0, self._jitter_us) * 1900))
                 self._launch_ps(g, final)
                 if final:
                     self.ev_ps_done.record(self.s_ps)

@@ -546,7 +546,8 @@ def _mp_worker(rank, world, port, cfg, out):
     torch.manual_seed(0)
     net = cfg.get("net", "ResNet18")
     eng = ShadowEngine(build_model(net, 10), rank, world, code=cfg["code"], svd_rank=3, lr=0.05, momentum=0.9,
-                       use_graph=cfg.get("graph", True), seed=5, ps_mode=cfg["ps_mode"], timeout_s=20.0)
+                       use_graph=cfg.get("graph", True), seed=5, ps_mode=cfg["ps_mode"], timeout_s=20.0,
+                       debug_jitter_us=cfg.get("jitter_us", 0.0))
     x, y = _batch(net, 32, seed=rank)
     eng.prepare(x, y, warmup=cfg.get("warmup", 2))
     losses = []
@@ -612,6 +613,26 @@ def test_shadow_engine_multi_gpu_replicas_identical(code, ps_mode):
         assert err == 0 and same, res
     trained = [r for r in res if not (ps_mode == "dedicated" and r[0] == 0)]
     assert all(r[4] < r[3] for r in trained), res
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("ps_mode", ["sharded", "colocated"])
+def test_shadow_engine_protocol_survives_random_delays(ps_mode):
+    """Protocol fuzzing (VERDICT r1 #5c): every rank sleeps a different random time (0-300 us, device side) before
+    each group's push and each PS launch, eager mode so the delays change every step.  The step-stamped flags must
+    still order everything: dense code == mean-gradient SGD exactly, replicas identical, no device error."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 8 else (8 if os.environ.get("ATOMO_TEST_WORLD8") else 2)
+    res = _run_mp(world, {"code": "sgd", "ps_mode": ps_mode, "graph": False, "check_dense": True, "steps": 6,
+                          "net": "VGG11", "warmup": 0, "jitter_us": 300.0}, 29870 + (3 if ps_mode == "sharded" else 0))
+    for r in res:
+        assert r[1] == 0 and r[2] and r[7], res
+    res = _run_mp(world, {"code": "svd", "ps_mode": ps_mode, "graph": False, "steps": 8, "jitter_us": 300.0},
+                  29890 + (3 if ps_mode == "sharded" else 0))
+    for r in res:
+        assert r[1] == 0 and r[2], res
 
 
 @pytest.mark.multigpu
