@@ -40,9 +40,13 @@ def run_baseline(args, rank, world, dev):
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = build_model(args.network, 10, "Cifar10").to(dev)
+    bf16 = getattr(args, "dtype", "fp32") == "bf16"     # same model-compute precision as the product arm when asked
     layout = FlatLayout.from_module(model)
     flat = torch.zeros(layout.total, device=dev)
     bind_parameters(model, flat, layout)
+    if bf16:
+        model = model.to(memory_format=torch.channels_last)
+        bind_parameters(model, flat, layout)
     is_ps = rank == 0
     is_worker = world == 1 or rank > 0
     nworkers = max(world - 1, 1)
@@ -66,7 +70,11 @@ def run_baseline(args, rank, world, dev):
             x = host_x.to(dev, non_blocking=True) if from_host else xd
             y = host_y.to(dev, non_blocking=True) if from_host else yd
             model.zero_grad(set_to_none=True)
-            loss = crit(model(x), y)
+            if bf16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = crit(model(x.contiguous(memory_format=torch.channels_last)).float(), y)
+            else:
+                loss = crit(model(x), y)
             loss.backward()
             codes = [enc.encode(p.grad) for p in model.parameters()]
             if from_host:
@@ -125,12 +133,14 @@ def run_baseline(args, rank, world, dev):
             "metric": "ResNet-18 CIFAR-10 images/sec (whole box, device-timed, max over ranks)",
             "value": round(imgs * args.steps / (ms / 1e3), 2), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bf16 else "fp32",
+            "data": "synthetic",
             "impl": "nccl-baseline",
             "config": {"model": args.network, "global_batch": imgs, "per_worker_batch": args.batch_size,
                        "parallelism": "dedicated ps + %d workers" % nworkers if world > 1 else "ps+worker on one gpu",
                        "code": code, "svd_rank": args.svd_rank,
-                       "stack": "torch.distributed NCCL send/recv/broadcast + torch.linalg.svd + eager fp32"},
+                       "stack": "torch.distributed NCCL send/recv/broadcast + torch.linalg.svd + eager %s" %
+                                ("bf16 autocast, NHWC" if bf16 else "fp32")},
             "e2e": {"value": round(imgs * args.steps / (ms_e2e / 1e3), 2), "unit": "images/s",
                     "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8, "d2h_bytes_per_step": 4},

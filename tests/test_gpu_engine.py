@@ -85,6 +85,8 @@ def _two_rank_worker(rank, world, code, port, out):
     for _ in range(20):
         losses.append(float(eng.train_step(x, y)[0]))
     torch.cuda.synchronize()
+    dist.barrier()           # the PS's last launch (stores into OUR copy) has completed
+    torch.cuda.synchronize()
     # every rank must hold identical parameters after the multicast / peer broadcast
     flat = eng.flat_params.clone()
     gathered = [torch.zeros_like(flat) for _ in range(world)]

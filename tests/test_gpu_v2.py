@@ -577,6 +577,8 @@ def _mp_worker(rank, world, port, cfg, out):
             ok_dense = ok_dense and bool(torch.allclose(got, ref["master"], rtol=2e-4, atol=2e-5)) and \
                 bool(torch.allclose(eng.vparams, ref["v"], rtol=2e-4, atol=2e-5))
     torch.cuda.synchronize()
+    dist.barrier()           # every owner's last PS launch (peer / multicast stores into OUR copy) has completed
+    torch.cuda.synchronize()
     ws = [torch.zeros_like(eng.wshadow) for _ in range(world)]
     dist.all_gather(ws, eng.wshadow.clone())
     vs = [torch.zeros_like(eng.vparams) for _ in range(world)]
