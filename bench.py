@@ -57,7 +57,10 @@ def parse():
     ap.add_argument("--no-overlap", dest="overlap", action="store_false", default=True)
     ap.add_argument("--optimizer", type=str, default="sgd", choices=["sgd", "adam"])
     ap.add_argument("--no-fp32-line", dest="fp32_line", action="store_false", default=True,
-                    help="skip the nested fp32 measurement of the same config (run in a child process per rank)")
+                    help="skip the nested fp32 measurement of the same config (run in a child process)")
+    ap.add_argument("--fp32-line-multi", action="store_true", default=False,
+                    help="also run the nested fp32 child when launched on more than one GPU (one child per rank, "
+                         "rendezvous on MASTER_PORT + 53); off by default: the scaling runs stay single-purpose")
     ap.add_argument("--ps-grid", type=int, default=0)
     ap.add_argument("--main-priority", type=int, default=0)
     ap.add_argument("--side-priority", type=int, default=-1)
@@ -317,7 +320,7 @@ def main():
     # Runs in a child process per rank (fresh CUDA context + symmetric heap; re-creating an NVLS binding inside
     # one process is avoided on purpose) through the fp32-flat engine; its JSON is nested under "fp32".
     fp32 = None
-    if args.fp32_line and args.dtype == "bf16" and args.impl == "atomo_b200":
+    if args.fp32_line and args.dtype == "bf16" and args.impl == "atomo_b200" and (world == 1 or args.fp32_line_multi):
         fp32 = fp32_child(args, rank, world)
     if rank == 0:
         if fp32 is not None:
@@ -331,12 +334,16 @@ def fp32_child(args, rank, world):
     torch.cuda.empty_cache()
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 53)
+    # Under torchrun every rank is a CLIENT of the elastic agent's store (TORCHELASTIC_USE_AGENT_STORE): on a new
+    # port nobody would serve and the children would block in the rendezvous (this hung an 8-GPU run for the full
+    # timeout).  Without the variable rank 0 of the children hosts its own TCPStore.
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)
     cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
            str(args.warmup), "--dtype", "fp32", "--engine", "fused", "--no-fp32-line", "--network", args.network,
            "--batch-size", str(args.batch_size), "--code", args.code, "--svd-rank", str(args.svd_rank), "--dataset",
            args.dataset, "--momentum", str(args.momentum), "--lr", str(args.lr)]
     try:
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     except Exception as e:  # noqa
         return {"unavailable": "fp32 child failed: %r" % (e,)}
     if rank != 0:
