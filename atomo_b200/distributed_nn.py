@@ -68,6 +68,7 @@ def run_rank(args) -> None:
     if world < 2:
         raise SystemExit("PS training needs world_size >= 2 (1 PS + >=1 worker); use single_machine for 1 process")
     comm = TorchDistTransport()
+    comm.enable_backup_rounds(args.num_aggregate)   # same answer on every rank: flag + backend + world size
 
     train_set, test_set, num_classes = build_datasets(
         args.dataset, args.data_root, synthetic=args.synthetic, seed=args.seed,
@@ -89,7 +90,14 @@ def run_rank(args) -> None:
         print("I am worker: {} in all {} workers, next step: {}".format(worker.rank, worker.world_size - 1, worker.next_step))
         worker.train(train_loader=train_loader, test_loader=test_loader)
         print("Worker Done Jobs! ...")
-    dist.barrier()
+    if comm.backup_rounds:
+        # STOP/bye already synchronised everyone; a collective barrier would hang on a lost worker
+        if not comm.clean_shutdown:          # a receive on a dead worker's connection is still pending
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+    else:
+        dist.barrier()
     dist.destroy_process_group()
 
 

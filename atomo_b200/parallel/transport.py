@@ -12,7 +12,12 @@ C3/C4 ``Bcast``       ``bcast_params(flat)``       (master:270-279, worker:275-2
 C7 ``isend(tag 88+i)````push(codes, step)``        (worker:330-335)
 C5/C6 ``irecv``/``waitany`` ``gather(step, need)`` (master:281-290, 198-214)
 C10 tag 77            ``send_kill(w)`` / ``kill_requested()``  (lenet.py:173-180)
+(none)                ``send_round(step, flat, need)`` / ``fetch_params(flat)`` / ``finish()``: backup-worker rounds
 ====================  =====================================================
+
+Backup workers (``--num-aggregate N`` < workers, gloo): see :mod:`atomo_b200.parallel.backup_rounds` — the PS announces
+a step point-to-point only to workers that owe it nothing, proceeds after ``N`` fresh gradients, never waits for a
+straggler, and keeps going when a worker's connection closes.
 
 :class:`TorchDistTransport` implements it over ``torch.distributed`` — gloo on
 CPU (BASELINE config 1) or NCCL on GPUs (the *baseline* the fused NVLink path
@@ -49,6 +54,19 @@ class Transport:
     def push(self, codes: list, step: int) -> int: raise NotImplementedError
     def gather(self, step: int, need: Optional[int] = None): raise NotImplementedError
     def send_kill(self, worker_rank: int) -> None: raise NotImplementedError
+    def enable_backup_rounds(self, need: int) -> bool: return False
+    def send_round(self, step: int, flat: torch.Tensor, need: Optional[int] = None) -> List[int]:
+        self.send_step(step)
+        self.bcast_params(flat)
+        return list(range(1, self.world_size))
+    def fetch_params(self, flat: torch.Tensor) -> None: self.bcast_params(flat)
+    def asked_workers(self) -> List[int]: return list(range(1, self.world_size))
+    def lost_workers(self) -> List[int]: return []
+    def finish(self) -> None:
+        self.drain()
+        self.send_step(STOP_STEP)
+    backup_rounds = False
+    clean_shutdown = True
     def drain(self) -> int: return 0
     def kill_requested(self, step=None) -> bool: return False
     def barrier(self) -> None: raise NotImplementedError
@@ -71,6 +89,8 @@ class TorchDistTransport(Transport):
         self._stale_dropped = 0
         self._rounds = 0                      # steps broadcast so far (PS side)
         self._recv_count: Dict[int, int] = {}  # messages received per worker (PS side)
+        self._p2p_rounds = False               # backup-worker rounds (parallel/backup_rounds.py)
+        self._backup = None
         self.bytes_sent = 0
 
     # -- step handshake -------------------------------------------------
@@ -85,11 +105,64 @@ class TorchDistTransport(Transport):
     def recv_step(self) -> int:
         t = torch.zeros(1, dtype=torch.int64, device=self.device)
         dist.recv(t, src=0, group=self.group, tag=10)
-        return int(t.item())
+        step = int(t.item())
+        if step == STOP_STEP and self._p2p_rounds:
+            # backup rounds: answer STOP with a bye on both receive channels of the PS (receiver thread + sentinel)
+            dist.send(torch.tensor([0, STOP_STEP], dtype=torch.int64, device=self.device), dst=0, group=self.group, tag=87)
+            dist.send(torch.zeros(1), dst=0, group=self.group, tag=99)
+        return step
 
     # -- parameters -------------------------------------------------------
     def bcast_params(self, flat: torch.Tensor) -> None:
         dist.broadcast(flat, src=0, group=self.group)
+
+    # -- backup-worker rounds (parallel/backup_rounds.py) ---------------------
+    def enable_backup_rounds(self, need: int) -> bool:
+        """Both roles call this with the same ``need`` before training.  True when steps will be announced
+        point-to-point (gloo and 0 < need < workers); NCCL has no any-source receive and keeps the collective
+        round, which waits for every worker."""
+        self._p2p_rounds = self.backend == "gloo" and 0 < int(need) < self.num_workers
+        if self._p2p_rounds and self.rank == 0:
+            from .backup_rounds import BackupRounds
+            self._backup = BackupRounds(self, need)
+        return self._p2p_rounds
+
+    @property
+    def backup_rounds(self) -> bool:
+        return self._p2p_rounds
+
+    def send_round(self, step: int, flat: torch.Tensor, need: Optional[int] = None) -> List[int]:
+        """PS: announce ``step`` and its parameters.  Returns the worker ranks that were asked for a gradient."""
+        if not self._p2p_rounds:
+            return super().send_round(step, flat, need)
+        return self._backup.send_round(step, flat)
+
+    def fetch_params(self, flat: torch.Tensor) -> None:
+        """Worker: receive the parameters of the step just announced."""
+        if self._p2p_rounds:
+            dist.recv(flat, src=0, group=self.group, tag=11)
+        else:
+            self.bcast_params(flat)
+
+    def asked_workers(self) -> List[int]:
+        """Workers that were announced the current step (late joiners included)."""
+        return sorted(self._backup.asked) if self._p2p_rounds else list(range(1, self.world_size))
+
+    def lost_workers(self) -> List[int]:
+        return sorted(self._backup.dead) if self._p2p_rounds and self.rank == 0 else []
+
+    def finish(self) -> None:
+        """PS: end of training — collect what stragglers still owe, then STOP every worker."""
+        if not self._p2p_rounds:
+            self.drain()
+            return self.send_step(STOP_STEP)
+        stop = torch.tensor([STOP_STEP], dtype=torch.int64, device=self.device)
+        self._backup.finish(lambda w: dist.send(stop, dst=w, group=self.group, tag=10))
+
+    @property
+    def clean_shutdown(self) -> bool:
+        """False when a worker was lost: a receive on its connection is still pending, skip the polite teardown."""
+        return self._backup.clean if self._p2p_rounds and self.rank == 0 else True
 
     # -- gradients: worker side ------------------------------------------
     def push(self, codes: list, step: int) -> int:
@@ -108,8 +181,16 @@ class TorchDistTransport(Transport):
         sender = dist.recv(hdr, src=src, group=self.group, tag=87)
         sender = src if src is not None else sender
         nbytes, msg_step = int(hdr[0].item()), int(hdr[1].item())
+        if nbytes == 0:                       # header-only message (the bye of a backup round)
+            return sender, msg_step, None
         buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        dist.recv(buf, src=sender, group=self.group, tag=88)
+        try:
+            dist.recv(buf, src=sender, group=self.group, tag=88)
+        except Exception as e:
+            if self._p2p_rounds:
+                from .backup_rounds import _PayloadLost
+                raise _PayloadLost(sender, e)
+            raise
         return sender, msg_step, buf
 
     def gather(self, step: int, need: Optional[int] = None):
@@ -123,6 +204,8 @@ class TorchDistTransport(Transport):
         surface in a later call.  A dead worker surfaces as the process-group
         timeout instead of the reference's infinite ``waitany`` block.
         """
+        if self._p2p_rounds:
+            return self._backup.gather(step, wire.unpack)
         need = self.num_workers if need is None else min(need, self.num_workers)
         got: Dict[int, list] = {}
         any_source = self.backend == "gloo"

@@ -138,20 +138,27 @@ class SyncReplicasMaster_NN(NN_Trainer):
             self.network.train()
             if self._verbose:
                 print("Master node is entering step: {}".format(i))
-            self.async_bcast_step()
-            self.async_bcast_layer_weights_bcast()
+            if self.comm.backup_rounds:
+                # backup workers: point-to-point announcement to the workers that owe nothing (transport.py)
+                self.comm.send_round(self.cur_step, self.flat_params, self._num_aggregate)
+            else:
+                self.async_bcast_step()
+                self.async_bcast_layer_weights_bcast()
 
             gather_start = time.time()
             coded_msgs = self.comm.gather(self.cur_step, need=self._num_aggregate)
             gather_duration = time.time() - gather_start
             if self._num_aggregate < self._num_workers:
-                # backup-worker mode: the update uses the first N arrivals; tell the stragglers to
-                # abandon the step (tag 77, lenet.py:173-180) and drop whatever they still send, so
-                # the collective broadcast of the next step cannot deadlock behind them
-                for w in range(1, self.world_size):
-                    if w not in coded_msgs and self._kwargs.get("kill_stragglers", False):
-                        self.comm.send_kill(w, self.cur_step)
-                self.comm.drain()
+                # backup-worker mode: the update uses the first N arrivals.  With --straggler-kill the others are
+                # told to abandon the step (tag 77, lenet.py:173-180).  Nobody is waited for: late messages are
+                # step-stamped and dropped when they surface; on NCCL (no any-source receive) gather() already
+                # waited for everyone.
+                if self._kwargs.get("kill_stragglers", False):
+                    for w in self.comm.asked_workers():
+                        if w not in coded_msgs:
+                            self.comm.send_kill(w, self.cur_step)
+                if not self.comm.backup_rounds:
+                    self.comm.drain()
 
             self._take_aux_buffers(coded_msgs)
             decode_start = time.time()
@@ -168,8 +175,7 @@ class SyncReplicasMaster_NN(NN_Trainer):
                 self.shrink_counter += 1
                 self.lr = self._base_lr * self._lr_shrinkage ** self.shrink_counter
                 self.optimizer.set_lr(self.lr)  # the reference never did this (master:232-234)
-        self.comm.drain()
-        self.comm.send_step(STOP_STEP)
+        self.comm.finish()      # collect what stragglers still owe, then STOP every worker
 
     def async_bcast_step(self):
         self.comm.send_step(self.cur_step)

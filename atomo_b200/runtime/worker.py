@@ -13,6 +13,7 @@ it, worker:319-323); the whole step's codes travel as one message.
 """
 from __future__ import annotations
 
+import os
 import time
 
 import torch
@@ -61,6 +62,15 @@ class DistributedWorker(NN_Trainer):
         self.device = torch.device("cuda", torch.cuda.current_device()) if self._enable_gpu else torch.device("cpu")
         self._coder = build_coder(kwargs, worker_side=True)
         self.last_stats = {}
+        # fault injection for the backup-worker tests: ATOMO_DEBUG_SLOW_WORKER="<rank>:<seconds per step>"
+        slow = os.environ.get("ATOMO_DEBUG_SLOW_WORKER", "")
+        self._debug_slow_s = float(slow.split(":")[1]) if slow and int(slow.split(":")[0]) == self.rank else 0.0
+        # ATOMO_DEBUG_DIE_WORKER="<rank>:<step>[,<rank>:<step>...]": the process exits in the middle of that step
+        self._debug_die_step = 0
+        for item in filter(None, os.environ.get("ATOMO_DEBUG_DIE_WORKER", "").split(",")):
+            r, st = item.split(":")
+            if int(r) == self.rank:
+                self._debug_die_step = int(st)
 
     def build_model(self, num_classes: int = 10):
         self.network = build_model(self.network_config, num_classes, self.dataset)
@@ -105,6 +115,11 @@ class DistributedWorker(NN_Trainer):
                 comp_start = time.time()
                 logits = self.network(x)
                 loss = self.criterion(logits, y)
+                if self._debug_slow_s:
+                    time.sleep(self._debug_slow_s)
+                if self._debug_die_step and self.cur_step == self._debug_die_step:
+                    print("Worker {}: fault injection, dying at step {}".format(self.rank, self.cur_step), flush=True)
+                    os._exit(0)
                 if self._split_backward:
                     emitted = {}
                     killed = self.network.backward_signal_kill(
@@ -140,7 +155,11 @@ class DistributedWorker(NN_Trainer):
                 if test_loader is not None and self.cur_step % self._eval_freq == 0:
                     self._evaluate_model(test_loader)
         # epochs exhausted before the PS stopped: keep answering until STOP
-        while self.async_fetch_step() != STOP_STEP:
+        while True:
+            self.next_step = self.async_fetch_step()
+            if self.next_step == STOP_STEP:
+                break
+            self.update_step()
             self.async_fetch_weights_bcast()
             self._send_grads([self._coder.encode(torch.zeros_like(p)) for p in self.network.parameters()])
 
@@ -155,7 +174,7 @@ class DistributedWorker(NN_Trainer):
         return changed
 
     def async_fetch_weights_bcast(self):
-        self.comm.bcast_params(self.flat_params)
+        self.comm.fetch_params(self.flat_params)     # broadcast, or point-to-point in backup-worker rounds
 
     def _encode(self):
         msgs, nbytes = [], 0

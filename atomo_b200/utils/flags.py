@@ -34,7 +34,8 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--dataset", type=str, default="MNIST", metavar="N")
     p.add_argument("--comm-type", type=str, default="Bcast", metavar="N")
     p.add_argument("--num-aggregate", type=int, default=0, metavar="N",
-                   help="gradients to wait for per step (0 = all workers; reference default 5 was a no-op)")
+                   help="gradients to wait for per step (0 = all workers; reference default 5 was a no-op).  N < workers = "
+                        "backup workers: the PS never waits for a straggler and keeps training when a worker is lost")
     p.add_argument("--eval-freq", type=int, default=50, metavar="N")
     p.add_argument("--train-dir", type=str, default="output/models/", metavar="N")
     p.add_argument("--compress", type=bool_flag, default=False)

@@ -207,3 +207,50 @@ def test_ps_checkpoint_of_a_bn_network_carries_trained_statistics(tmp_path):
     assert float(sd["bn1.running_mean"].abs().sum()) > 0
     assert not torch.allclose(sd["bn1.running_var"], torch.ones_like(sd["bn1.running_var"]))
     assert int(sd["bn1.num_batches_tracked"]) >= 2
+
+
+def _run_backup(extra, env_extra, port, nproc=3, steps=12, need=1, code=("--code", "sgd")):
+    cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
+           "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64",
+           "--nproc", str(nproc), "--network", "LeNet", "--dataset", "MNIST", *code, "--max-steps", str(steps),
+           "--num-aggregate", str(need), "--master-port", str(port)] + extra
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+               **env_extra)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_backup_workers_do_not_wait_for_a_straggler(tmp_path):
+    """with --num-aggregate 1 of 2 the PS used to drain every straggler message before the next step,
+    so each step still cost the slowest worker's time.  Rounds are now announced point-to-point to the workers that
+    owe nothing (parallel/backup_rounds.py): a worker that sleeps 0.5 s per step must not slow the PS down, its late
+    gradients are dropped, and it rejoins with the CURRENT parameters (so it logs far fewer steps than the fast
+    worker, and the steps it does log are not consecutive replays)."""
+    import re
+    out = _run_backup(["--eval-freq", "100", "--train-dir", str(tmp_path) + "/"],
+                      {"ATOMO_DEBUG_SLOW_WORKER": "2:0.5"}, 29597)
+    assert "Master: Step: 12" in out
+    gathers = [float(m.group(1)) for m in re.finditer(r"Master: Step: \d+, .*Gather: ([0-9.e-]+)", out)]
+    assert len(gathers) == 12
+    assert sum(gathers[1:]) < 0.5 * 11 * 0.5, gathers       # never the straggler's 0.5 s per step
+    fast = [int(m.group(1)) for m in re.finditer(r"Worker: 1, Step: (\d+),", out)]
+    slow = [int(m.group(1)) for m in re.finditer(r"Worker: 2, Step: (\d+),", out)]
+    # the fast worker is handed the current step the moment its previous message lands: it takes part in every step
+    assert fast == list(range(1, 13)), fast
+    assert 1 <= len(slow) < 6, slow
+
+
+def test_ps_survives_lost_workers_in_backup_mode(tmp_path):
+    """SURVEY 5.3 (the reference's PS blocks forever in waitany when a worker dies): with --num-aggregate 2 of 3,
+    worker 2 dies in step 3 and worker 3 in step 5.  The PS notices each closed connection, keeps training with the
+    survivors (need shrinks to 1), writes its checkpoints and shuts down cleanly."""
+    d = str(tmp_path) + "/"
+    out = _run_backup(["--eval-freq", "4", "--train-dir", d], {"ATOMO_DEBUG_DIE_WORKER": "2:3,3:5"}, 29598,
+                      nproc=4, steps=8, need=2, code=("--code", "svd", "--svd-rank", "2"))
+    assert "Master: worker 2 is gone" in out and "Master: worker 3 is gone" in out
+    assert "Master: Step: 8" in out
+    # worker 1 may miss the cut of an early step (2 of 3 are enough) but it carries steps 6..8 alone
+    assert all("Worker: 1, Step: %d," % s in out for s in (6, 7, 8))
+    assert "Done sending messages to workers!" in out
+    assert os.path.isfile(d + "model_step_8") and os.path.isfile(d + "model_step_8_optim")
