@@ -107,3 +107,20 @@ def test_resnet18_unit_kinds():
             assert u.cols == 18 and u.rcap == 8 and u.budget == 3.0
     dense = P.build_plan2(_shapes("ResNet18"), "sgd", 3)
     assert all(u.kind in (P.KIND_DENSE16, P.KIND_VEC) for u in dense.units) and dense.n_coded == 0
+
+
+@pytest.mark.parametrize("net,ds,ncls,rank", [("ResNet18", "Cifar10", 10, 3), ("ResNet50", "ImageNet", 1000, 8),
+                                              ("VGG11", "Cifar10", 10, 3)])
+def test_sharded_owners_carry_equal_shares(net, ds, ncls, rank):
+    """Sharded PS: tile j of a group goes to owner j % n_owners.  Every GPU must end up with the same share of the
+    update work (elements reconstructed + updated + multicast), otherwise the slowest owner is the step's tail."""
+    from atomo_b200.models import build_model
+    shapes = [tuple(p.shape) for p in build_model(net, ncls, ds).parameters()]
+    for owners in (2, 4, 8):
+        pl = P.build_plan2(shapes, "svd", rank, False, n_owners=owners, n_groups=5)
+        load = [0] * owners
+        for (u, a, b, o) in pl.ps_tiles:
+            un = pl.units[u]
+            load[o] += b * un.cols if un.kind in (P.KIND_SLAB, P.KIND_MAT) else b
+        assert sum(load) == sum(q.numel for q in pl.params)      # every element has exactly one owner
+        assert max(load) <= 1.05 * sum(load) / owners, (net, owners, load)
