@@ -86,8 +86,12 @@ def sample_atoms(
     uniforms: Optional[torch.Tensor] = None,
     max_atoms: Optional[int] = None,
     max_tries: int = 64,
+    allow_empty: bool = False,
 ) -> torch.Tensor:
     """Return the (sorted) indices of the kept atoms.
+
+    ``allow_empty=True`` accepts a draw that keeps nothing (the unbiased choice: the reference's redraw-until-
+    non-empty, svd.py:65-66, over-weights small budgets; the sm_100a engine does not redraw either).
 
     ``uniforms`` (same length as ``probs`` for bernoulli, length >= 1 for
     systematic) overrides the RNG — the CUDA kernels accept the same override
@@ -107,7 +111,7 @@ def sample_atoms(
             cnt = int(keep.sum())
             # reference: resample when nothing was selected (svd.py:65-66);
             # the fixed-slot GPU path additionally resamples on overflow.
-            if cnt == 0 and float(p.max()) > 0:
+            if cnt == 0 and float(p.max()) > 0 and not allow_empty:
                 continue
             if max_atoms is not None and cnt > max_atoms:
                 continue

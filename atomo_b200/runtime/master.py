@@ -45,6 +45,10 @@ def build_coder(kwargs: dict, worker_side: bool):
     if code == "entrywise":
         return codings.build("entrywise", budget=kwargs.get("entry_budget", 0.05),
                              prob_rule=kwargs.get("prob_rule", "reference"))
+    if code == "bsvd":
+        return codings.build("bsvd", rank=kwargs.get("svd_rank", 0) or 3, random_sample=worker_side,
+                             prob_rule=kwargs.get("prob_rule", "reference"),
+                             scheme=kwargs.get("sampling", "bernoulli"))
     if code == "qsvd":
         return codings.build("qsvd", rank=kwargs.get("svd_rank", 0), random_sample=worker_side,
                              quantization_level=kwargs.get("quantization_level", 4),

@@ -29,7 +29,8 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--log-interval", type=int, default=10, metavar="N")
     p.add_argument("--network", type=str, default="LeNet", metavar="N")
     p.add_argument("--code", type=str, default="sgd",
-                   help="sgd | svd | qsgd | terngrad | entrywise | qsvd")
+                   help="sgd | svd | qsgd | terngrad | entrywise | qsvd | bsvd (block-spectral: the estimator the sm_100a "
+                        "bf16 engine applies under --code svd, as a plain PyTorch coder)")
     p.add_argument("--bucket-size", type=int, default=512)
     p.add_argument("--dataset", type=str, default="MNIST", metavar="N")
     p.add_argument("--comm-type", type=str, default="Bcast", metavar="N")

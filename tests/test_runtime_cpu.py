@@ -118,7 +118,7 @@ def test_baseline_config1_lenet_entrywise_gloo_world2(tmp_path):
 
 
 @pytest.mark.parametrize("code,extra", [("svd", ["--svd-rank", "3"]), ("qsgd", ["--quantization-level", "4"]),
-                                        ("sgd", []), ("qsvd", ["--svd-rank", "2"])])
+                                        ("sgd", []), ("qsvd", ["--svd-rank", "2"]), ("bsvd", ["--svd-rank", "4"])])
 def test_three_rank_gloo_all_coders(code, extra, tmp_path):
     out = _run_launcher(["--nproc", "3", "--network", "LeNet", "--dataset", "MNIST", "--code", code,
                          "--max-steps", "4", "--eval-freq", "100", "--train-dir", str(tmp_path) + "/",
