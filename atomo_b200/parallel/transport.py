@@ -91,6 +91,7 @@ class TorchDistTransport(Transport):
         self._recv_count: Dict[int, int] = {}  # messages received per worker (PS side)
         self._p2p_rounds = False               # backup-worker rounds (parallel/backup_rounds.py)
         self._backup = None
+        self._bye_on_stop = False
         self.bytes_sent = 0
 
     # -- step handshake -------------------------------------------------
@@ -107,9 +108,10 @@ class TorchDistTransport(Transport):
         dist.recv(t, src=0, group=self.group, tag=10)
         step = int(t.item())
         if step == STOP_STEP and self._p2p_rounds:
-            # backup rounds: answer STOP with a bye on both receive channels of the PS (receiver thread + sentinel)
+            # backup rounds: answer STOP with a bye on the receiver thread's channel (the sentinel's follows)
             dist.send(torch.tensor([0, STOP_STEP], dtype=torch.int64, device=self.device), dst=0, group=self.group, tag=87)
-            dist.send(torch.zeros(1), dst=0, group=self.group, tag=99)
+        if step == STOP_STEP and self._bye_on_stop:
+            dist.send(torch.zeros(1), dst=0, group=self.group, tag=99)     # completes the PS's sentinel receive
         return step
 
     # -- parameters -------------------------------------------------------
@@ -122,10 +124,34 @@ class TorchDistTransport(Transport):
         point-to-point (gloo and 0 < need < workers); NCCL has no any-source receive and keeps the collective
         round, which waits for every worker."""
         self._p2p_rounds = self.backend == "gloo" and 0 < int(need) < self.num_workers
+        self._bye_on_stop = self.backend == "gloo"
         if self._p2p_rounds and self.rank == 0:
             from .backup_rounds import BackupRounds
             self._backup = BackupRounds(self, need)
+        elif self.backend == "gloo" and self.rank == 0:
+            self._start_fail_fast_watch()
         return self._p2p_rounds
+
+    def _start_fail_fast_watch(self) -> None:
+        """All-workers mode on gloo: the PS cannot continue without a worker (collective broadcast, gather of W
+        gradients), and a blocked any-source receive would only notice after the process-group timeout (30 min; the
+        reference: never, master:198-214).  One sentinel receive per worker completes with an error the moment that
+        worker's connection closes: report it and stop the job at once."""
+        import os
+        import sys
+        import threading
+
+        def watch(w):
+            try:
+                dist.recv(torch.zeros(1), src=w, group=self.group, tag=99)     # completes normally with the bye
+            except Exception as e:
+                print("Master: worker {} is gone ({}): stopping the job.  With --num-aggregate N < workers the PS "
+                      "keeps training with the survivors.".format(w, str(e).strip().splitlines()[-1][-80:]), flush=True)
+                sys.stderr.flush()
+                os._exit(3)
+
+        for w in range(1, self.world_size):
+            threading.Thread(target=watch, args=(w,), daemon=True).start()
 
     @property
     def backup_rounds(self) -> bool:

@@ -254,3 +254,21 @@ def test_ps_survives_lost_workers_in_backup_mode(tmp_path):
     assert all("Worker: 1, Step: %d," % s in out for s in (6, 7, 8))
     assert "Done sending messages to workers!" in out
     assert os.path.isfile(d + "model_step_8") and os.path.isfile(d + "model_step_8_optim")
+
+
+def test_ps_fails_fast_when_a_worker_dies_in_all_workers_mode(tmp_path):
+    """Without backup workers the PS needs every gradient: a dead worker must stop the job at once with a clear
+    message (the reference blocks forever in waitany; a plain gloo receive would wait for the 30-minute timeout)."""
+    import time
+    cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
+           "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64", "--nproc", "3",
+           "--network", "LeNet", "--dataset", "MNIST", "--code", "sgd", "--max-steps", "50", "--eval-freq", "100",
+           "--train-dir", str(tmp_path) + "/", "--master-port", "29599"]
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+               ATOMO_DEBUG_DIE_WORKER="2:3")
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode != 0
+    assert "Master: worker 2 is gone" in r.stdout and "stopping the job" in r.stdout
+    assert "Master: Step: 2," in r.stdout and "Master: Step: 4," not in r.stdout
+    assert time.time() - t0 < 120
