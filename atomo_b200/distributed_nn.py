@@ -114,7 +114,22 @@ def main(argv=None):
     args = add_fit_args(argparse.ArgumentParser(description="atomo_b200 distributed PS trainer"), argv)
     if args.nproc and "RANK" not in os.environ:
         import torch.multiprocessing as mp
-        mp.spawn(_spawn_entry, args=(args, args.nproc), nprocs=args.nproc, join=True)
+        attempt = 0
+        while True:
+            try:
+                mp.spawn(_spawn_entry, args=(args, args.nproc), nprocs=args.nproc, join=True)
+                break
+            except Exception as e:  # a rank raised or exited non-zero (e.g. the PS stopped the job: a worker is gone)
+                attempt += 1
+                if attempt > args.max_restarts:
+                    raise
+                # checkpoint/resume-based recovery (the reference has neither): the PS state
+                # (weights, optimizer, step, LR schedule) comes back from model_step_<N> + its _optim sidecar,
+                # workers get parameters from the PS at every step anyway
+                print("launcher: job failed ({}); restart {}/{} from the latest checkpoint in {}".format(
+                    str(e).strip().splitlines()[0][:120], attempt, args.max_restarts, args.train_dir), flush=True)
+                args.resume = True
+                args.master_port += 1          # the old rendezvous port may still be in TIME_WAIT
     else:
         run_rank(args)
 

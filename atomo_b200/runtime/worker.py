@@ -72,6 +72,16 @@ class DistributedWorker(NN_Trainer):
             if int(r) == self.rank:
                 self._debug_die_step = int(st)
 
+    def _die_armed(self) -> bool:
+        """ATOMO_DEBUG_DIE_ONCE=<marker file>: the injected death happens once per marker (restart tests)."""
+        marker = os.environ.get("ATOMO_DEBUG_DIE_ONCE", "")
+        if not marker:
+            return True
+        if os.path.exists(marker):
+            return False
+        open(marker, "w").close()
+        return True
+
     def build_model(self, num_classes: int = 10):
         self.network = build_model(self.network_config, num_classes, self.dataset)
         if self._split_backward:
@@ -117,7 +127,7 @@ class DistributedWorker(NN_Trainer):
                 loss = self.criterion(logits, y)
                 if self._debug_slow_s:
                     time.sleep(self._debug_slow_s)
-                if self._debug_die_step and self.cur_step == self._debug_die_step:
+                if self._debug_die_step and self.cur_step == self._debug_die_step and self._die_armed():
                     print("Worker {}: fault injection, dying at step {}".format(self.rank, self.cur_step), flush=True)
                     os._exit(0)
                 if self._split_backward:

@@ -58,6 +58,10 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--weight-decay", type=float, default=0.0)
     p.add_argument("--nesterov", type=bool_flag, default=False)
     p.add_argument("--resume", type=bool_flag, default=False)
+    p.add_argument("--max-restarts", type=int, default=0,
+                   help="--nproc self-spawn: when the job fails (a rank died, the PS stopped it), relaunch it up to N "
+                        "times from the latest checkpoint (--resume 1 is implied for the relaunches).  Under torchrun "
+                        "use its own --max-restarts together with --resume 1")
     p.add_argument("--dtype", type=str, default="fp32", choices=["fp32", "bf16"])
     p.add_argument("--ps-mode", type=str, default="sharded", choices=["sharded", "colocated", "dedicated"],
                    help="p2p backend: sharded = every GPU trains and owns 1/N of the PS tiles (bf16 engine); "

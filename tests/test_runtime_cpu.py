@@ -272,3 +272,22 @@ def test_ps_fails_fast_when_a_worker_dies_in_all_workers_mode(tmp_path):
     assert "Master: worker 2 is gone" in r.stdout and "stopping the job" in r.stdout
     assert "Master: Step: 2," in r.stdout and "Master: Step: 4," not in r.stdout
     assert time.time() - t0 < 120
+
+
+def test_launcher_restarts_from_the_latest_checkpoint(tmp_path):
+    """--max-restarts: worker 2 dies in step 5 (once), the PS stops the job, the launcher relaunches it with --resume
+    and training continues from the step-4 checkpoint to the end."""
+    d = str(tmp_path) + "/"
+    cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
+           "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64", "--nproc", "3",
+           "--network", "LeNet", "--dataset", "MNIST", "--code", "svd", "--svd-rank", "2", "--max-steps", "8",
+           "--eval-freq", "2", "--train-dir", d, "--master-port", "29601", "--max-restarts", "2"]
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+               ATOMO_DEBUG_DIE_WORKER="2:5", ATOMO_DEBUG_DIE_ONCE=str(tmp_path / "died"))
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "Master: worker 2 is gone" in out and "restart 1/2 from the latest checkpoint" in out
+    assert out.count("Master: Step: 4,") == 1          # not replayed: the relaunch starts at step 5
+    assert out.count("Master: Step: 5,") == 1 and "Master: Step: 8," in out
+    assert os.path.isfile(d + "model_step_8")
