@@ -610,7 +610,8 @@ def test_shadow_engine_multi_gpu_replicas_identical(code, ps_mode):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 8 else (8 if os.environ.get("ATOMO_TEST_WORLD8") else 2)
-    res = _run_mp(world, {"code": code, "ps_mode": ps_mode}, 29700 + abs(hash((code, ps_mode))) % 200)
+    port = 29700 + 7 * ["sharded", "colocated", "dedicated"].index(ps_mode) + (3 if code == "sgd" else 0)
+    res = _run_mp(world, {"code": code, "ps_mode": ps_mode}, port)
     for rank, err, same, l0, l1, mode, mc, _ in res:
         assert err == 0 and same, res
     trained = [r for r in res if not (ps_mode == "dedicated" and r[0] == 0)]
