@@ -58,3 +58,42 @@ def test_data_prepare_and_sv_decay_tools(tmp_path, capsys):
     rows = sv.main(["--network", "LeNet", "--layer", "conv2.weight", "--steps", "2", "--every", "1",
                     "--batch-size", "8"])
     assert len(rows) == 3 and len(rows[0][1]) == 50 and rows[0][1][0] == 1.0  # (500, 50) matricization
+
+
+def test_p2p_launcher_engine_selection(monkeypatch):
+    """--backend p2p: bf16 + svd|qsvd|sgd runs the overlapped sharded engine, everything else the fp32-flat engine;
+    asking the fp32-flat engine for Adam is refused instead of silently training with SGD."""
+    import argparse
+    import sys
+    import types
+    from atomo_b200.runtime import p2p_launcher as L
+    from atomo_b200.utils.flags import add_fit_args
+
+    made = []
+
+    class Fake:
+        def __init__(self, *a, **kw):
+            made.append((type(self).__name__, kw))
+
+    shadow = types.ModuleType("atomo_b200.runtime.shadow_engine")
+    shadow.ShadowEngine = type("ShadowEngine", (Fake,), {})
+    fused = types.ModuleType("atomo_b200.runtime.engine")
+    fused.FusedEngine = type("FusedEngine", (Fake,), {})
+    monkeypatch.setitem(sys.modules, "atomo_b200.runtime.shadow_engine", shadow)
+    monkeypatch.setitem(sys.modules, "atomo_b200.runtime.engine", fused)
+
+    def args(*argv):
+        return add_fit_args(argparse.ArgumentParser(), list(argv))
+
+    _, kind = L._build_engine(args("--dtype", "bf16", "--code", "svd", "--svd-rank", "3", "--num-aggregate", "2"), None, 0, 4)
+    assert kind == "shadow" and made[-1][0] == "ShadowEngine"
+    assert made[-1][1]["ps_mode"] == "sharded" and made[-1][1]["num_aggregate"] == 2 and made[-1][1]["groups"] == 5
+    _, kind = L._build_engine(args("--dtype", "bf16", "--code", "qsvd", "--optimizer", "adam"), None, 0, 2)
+    assert kind == "shadow" and made[-1][1]["optimizer"] == "adam" and made[-1][1]["code"] == "qsvd"
+    _, kind = L._build_engine(args("--dtype", "bf16", "--code", "qsgd"), None, 0, 2)
+    assert kind == "fused" and made[-1][0] == "FusedEngine" and made[-1][1]["ps_mode"] == "colocated"
+    _, kind = L._build_engine(args("--dtype", "fp32", "--code", "svd", "--ps-mode", "dedicated"), None, 0, 2)
+    assert kind == "fused" and made[-1][1]["ps_mode"] == "dedicated" and made[-1][1]["dtype"] == "fp32"
+    import pytest
+    with pytest.raises(SystemExit):
+        L._build_engine(args("--dtype", "fp32", "--code", "svd", "--optimizer", "adam"), None, 0, 2)
