@@ -58,6 +58,9 @@ class NN_Trainer:
         self.device = torch.device(kwargs.get("device", "cpu"))
         self.fetch_indicator = kwargs.get("fetch_indicator", False)
         self.log_interval = kwargs.get("log_interval", 10)
+        # optional: pass every gradient through a coder (encode -> decode) before the optimizer step: the effect of
+        # a sparsifier on training, without a cluster (one worker, so no averaging of independent draws)
+        self.coder = kwargs.get("coder", None)
 
     def build_model(self, num_classes: int = 10):
         self.network = build_model(self.network_config, num_classes, self.dataset).to(self.device)
@@ -79,6 +82,10 @@ class NN_Trainer:
                 if self.fetch_indicator:
                     for p in self.network.parameters():
                         svd_encode(p.grad, step)
+                if self.coder is not None:
+                    for p in self.network.parameters():
+                        g = self.coder.decode(self.coder.encode(p.grad.detach().float()))
+                        p.grad = g.reshape(p.shape).to(p.grad.device, p.grad.dtype)
                 self.optimizer.step()
                 prec1, prec5 = accuracy(logits, y, topk=(1, 5))
                 step += 1

@@ -30,6 +30,12 @@ def main(argv=None):
     ap.add_argument("--train-len", type=int, default=0)
     ap.add_argument("--test-len", type=int, default=0)
     ap.add_argument("--fetch-indicator", type=bool_flag, default=False)
+    ap.add_argument("--code", type=str, default="",
+                    help="pass every gradient through this coder (svd | bsvd | qsvd | qsgd | terngrad | entrywise) "
+                         "before the optimizer step: what a sparsifier does to training, without a cluster")
+    ap.add_argument("--svd-rank", type=int, default=3)
+    ap.add_argument("--quantization-level", type=int, default=4)
+    ap.add_argument("--entry-budget", type=float, default=0.05)
     args = ap.parse_args(argv)
 
     torch.manual_seed(args.seed)
@@ -38,7 +44,12 @@ def main(argv=None):
                                        args.train_len or None, args.test_len or None)
     train_loader = torch.utils.data.DataLoader(train, batch_size=args.batch_size, shuffle=True)
     test_loader = torch.utils.data.DataLoader(test, batch_size=args.test_batch_size, shuffle=False)
-    trainer = NN_Trainer(batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs,
+    coder = None
+    if args.code and args.code not in ("sgd", "dense"):
+        from .runtime.master import build_coder
+        coder = build_coder({"code": args.code, "svd_rank": args.svd_rank, "entry_budget": args.entry_budget,
+                             "quantization_level": args.quantization_level}, worker_side=True)
+    trainer = NN_Trainer(coder=coder, batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs,
                          momentum=args.momentum, network=args.network, dataset=args.dataset, device=device,
                          fetch_indicator=args.fetch_indicator, log_interval=args.log_interval)
     trainer.build_model(num_classes=ncls)

@@ -156,6 +156,15 @@ def test_single_machine_and_tuning_parser(tmp_path):
     assert tp_main(["--tuning-dir", str(tmp_path), "--tuning-lr", "0.01", "--num-workers", "3"]) == pytest.approx(3.0)
 
 
+def test_single_machine_with_a_coder_in_the_loop():
+    from atomo_b200.single_machine import main as sm_main
+    for code in ("bsvd", "entrywise"):
+        res = sm_main(["--network", "LeNet", "--dataset", "MNIST", "--synthetic", "1", "--train-len", "256",
+                       "--test-len", "64", "--batch-size", "32", "--max-steps", "8", "--test-batch-size", "64",
+                       "--lr", "0.02", "--code", code, "--svd-rank", "3", "--entry-budget", "0.2"])
+        assert 0 < res["loss"] < 2.4
+
+
 def test_data_sharding_and_loader():
     from atomo_b200.data import DataLoader, build_datasets, shard_indices
     a, b = shard_indices(100, 0, 2, seed=3), shard_indices(100, 1, 2, seed=3)
