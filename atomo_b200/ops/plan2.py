@@ -291,7 +291,9 @@ def build_plan2(shapes: Sequence[Sequence[int]], code: str = "svd", rank: int = 
                 rows, cols, rs, cs = o, i, i, 1
             else:
                 rows, cols, rs, cs = i, o, 1, i
-            if cols >= 2:
+            # a trailing 1-column block (cols % block_cols == 1) has no eigenproblem to solve: such tensors (none in
+            # the model zoo) travel dense instead of exercising a degenerate unit in the kernels
+            if cols >= 2 and cols % block_cols != 1:
                 nb = (cols + block_cols - 1) // block_cols
                 bud = float(rank) if nb == 1 else float(max(1, -(-rank // nb)))
                 for b in range(nb):
