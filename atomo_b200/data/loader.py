@@ -29,6 +29,9 @@ class DataLoader:
         self._loader = _TorchLoader(dataset, batch_size=batch_size, shuffle=shuffle, num_workers=num_workers,
                                     drop_last=drop_last, generator=self._gen, pin_memory=False,
                                     persistent_workers=num_workers > 0)
+        if len(self._loader) == 0:
+            raise ValueError("DataLoader: %d samples give no batch of %d with drop_last=%s (a worker's shard is "
+                             "smaller than --batch-size?)" % (len(dataset), batch_size, drop_last))
         self._iter: Optional[Iterator] = None
         self.epochs_completed = 0
         self._prefetch = max(int(prefetch), 0)
