@@ -97,3 +97,29 @@ def test_p2p_launcher_engine_selection(monkeypatch):
     import pytest
     with pytest.raises(SystemExit):
         L._build_engine(args("--dtype", "fp32", "--code", "svd", "--optimizer", "adam"), None, 0, 2)
+
+
+def test_worker_log_line_roundtrips_through_the_tuning_parser():
+    """The worker line is a de-facto API (the LR grid search greps it): whatever the trainer can print — diverged
+    losses included — the parser must read back."""
+    from hypothesis import given, settings, strategies as st
+    from atomo_b200.tiny_tuning_parser import parse_line
+    from atomo_b200.utils.logging import worker_line
+
+    pos = st.floats(0, 1e4, allow_nan=False)
+
+    @settings(max_examples=200, deadline=None)
+    @given(rank=st.integers(0, 64), step=st.integers(0, 10 ** 7), epoch=st.integers(0, 999), seen=st.integers(0, 10 ** 6),
+           total=st.integers(1, 10 ** 7), loss=st.one_of(st.floats(-1e3, 1e6, allow_nan=False), st.just(float("nan")),
+                                                           st.just(float("inf"))),
+           t=pos, comp=pos, enc=pos, comm=pos, mb=pos, p1=st.floats(0, 100), p5=st.floats(0, 100))
+    def check(rank, step, epoch, seen, total, loss, t, comp, enc, comm, mb, p1, p5):
+        rec = parse_line(worker_line(rank, step, epoch, seen, total, loss, t, comp, enc, comm, mb, p1, p5))
+        assert rec is not None and rec["worker"] == rank and rec["step"] == step
+        if loss == loss and abs(loss) != float("inf"):
+            assert abs(rec["loss"] - loss) <= 5e-5 + 1e-9 * abs(loss)
+        else:
+            assert rec["loss"] != rec["loss"] or abs(rec["loss"]) == float("inf")
+        assert abs(rec["msg_mb"] - mb) <= 5e-5 and abs(rec["prec1"] - p1) <= 5e-5
+
+    check()
