@@ -32,6 +32,7 @@ def _kwargs(args, role: str) -> dict:
         "code": args.code, "svd_rank": args.svd_rank, "quantization_level": args.quantization_level,
         "bucket_size": args.bucket_size, "entry_budget": args.entry_budget, "sampling": args.sampling,
         "prob_rule": args.prob_rule, "eval_batches": args.eval_batches or None,
+        "metrics_file": args.metrics_file,
     }
     if role == "master":
         kw.update({"num_aggregate": args.num_aggregate, "lr_shrinkage": args.lr_shrinkage,

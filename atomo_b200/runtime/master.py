@@ -23,7 +23,7 @@ from ..models import build_model
 from ..optim import SGD, Adam
 from ..parallel.transport import Transport, STOP_STEP
 from ..utils import checkpoint as ckpt
-from ..utils.logging import master_line
+from ..utils.logging import MetricsWriter, master_line
 from .flat import FlatLayout, bind_parameters
 from .nn_ops import NN_Trainer
 
@@ -108,6 +108,7 @@ class SyncReplicasMaster_NN(NN_Trainer):
         self.device = torch.device("cuda", torch.cuda.current_device()) if self._enable_gpu else torch.device("cpu")
         self._coder = build_coder(kwargs, worker_side=False)
         self._kwargs = kwargs
+        self._metrics = MetricsWriter(kwargs.get("metrics_file", ""), 0, "ps")
 
     def build_model(self, num_classes: int = 10):
         self.network = build_model(self.network_config, num_classes, self.dataset).to(self.device)
@@ -169,6 +170,9 @@ class SyncReplicasMaster_NN(NN_Trainer):
             n_used = self._decode(coded_msgs)
             decode_dur = time.time() - decode_start
             print(master_line(self.cur_step, decode_dur, self.lr, gather_duration))
+            self._metrics.write(step=self.cur_step, gather=gather_duration, decode=decode_dur, lr=self.lr,
+                                used_workers=sorted(coded_msgs), stale_dropped=getattr(self.comm, "_stale_dropped", 0),
+                                lost_workers=self.comm.lost_workers())
             self._model_update(n_used)
             self.grad_accumulator.meset_everything()
 

@@ -45,7 +45,7 @@ def run_p2p_training(args):
     from ..data import DataLoader, build_datasets, shard_dataset
     from ..models import build_model
     from ..utils import checkpoint as ckpt
-    from ..utils.logging import master_line, test_line, worker_line
+    from ..utils.logging import MetricsWriter, master_line, test_line, worker_line
     from .nn_ops import accuracy
 
     rank = int(os.environ.get("RANK", "0"))
@@ -63,6 +63,7 @@ def run_p2p_training(args):
         train_len=args.train_len or None, test_len=args.test_len or None)
     model = build_model(args.network, num_classes, args.dataset)
     eng, kind = _build_engine(args, model, rank, world)
+    metrics = MetricsWriter(getattr(args, "metrics_file", ""), rank, "p2p")
     first = eng.first_worker
     nworkers = eng.W
     shard = shard_dataset(train_set, max(rank - first, 0), nworkers, seed=args.seed)
@@ -115,6 +116,8 @@ def run_p2p_training(args):
                                   step_s, comp, enc, comm, msg_mb, p1, p5))
             if eng.is_ps or (kind == "shadow" and eng.is_owner):
                 print(master_line(cur, ph.get("ps_work_us", 0.0) / 1e6, eng.lr, ph.get("ps_wait_push_us", 0.0) / 1e6))
+            metrics.write(step=cur, loss=loss, prec1=p1, prec5=p5, step_s=step_s, comp=comp, encode=enc, comm=comm,
+                          msg_mb=msg_mb, lr=eng.lr, phase_us={k: round(float(v), 1) for k, v in ph.items()})
             ev_a.record()
             since = 0
         if cur % args.eval_freq == 0:
@@ -149,6 +152,7 @@ def run_p2p_training(args):
     if err:
         print("rank %d: device error code %d" % (rank, err))
     loader.close()
+    metrics.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()

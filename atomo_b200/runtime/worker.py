@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from ..models import build_model
 from ..parallel.transport import Transport, STOP_STEP
 from ..utils import checkpoint as ckpt
-from ..utils.logging import worker_line, test_line
+from ..utils.logging import MetricsWriter, worker_line, test_line
 from .flat import FlatLayout, bind_parameters
 from .master import STEP_START_, build_coder
 from .nn_ops import NN_Trainer, accuracy
@@ -62,6 +62,7 @@ class DistributedWorker(NN_Trainer):
         self.device = torch.device("cuda", torch.cuda.current_device()) if self._enable_gpu else torch.device("cpu")
         self._coder = build_coder(kwargs, worker_side=True)
         self.last_stats = {}
+        self._metrics = MetricsWriter(kwargs.get("metrics_file", ""), self.rank, "worker")
         # fault injection for the backup-worker tests: ATOMO_DEBUG_SLOW_WORKER="<rank>:<seconds per step>"
         slow = os.environ.get("ATOMO_DEBUG_SLOW_WORKER", "")
         self._debug_slow_s = float(slow.split(":")[1]) if slow and int(slow.split(":")[0]) == self.rank else 0.0
@@ -162,6 +163,10 @@ class DistributedWorker(NN_Trainer):
                 print(worker_line(self.rank, self.cur_step, num_epoch, batch_idx * self.batch_size, n_data,
                                   loss.item(), time.time() - iter_start, comp_dur, encode_dur, comm_dur,
                                   msg_bytes / (1024.0 ** 2), prec1.item(), prec5.item()))
+                self._metrics.write(step=self.cur_step, epoch=num_epoch, loss=float(loss.item()),
+                                    time=time.time() - iter_start, comp=comp_dur, encode=encode_dur, comm=comm_dur,
+                                    fetch=fetch_weight_duration, msg_mb=msg_bytes / (1024.0 ** 2),
+                                    prec1=float(prec1.item()), prec5=float(prec5.item()))
                 if test_loader is not None and self.cur_step % self._eval_freq == 0:
                     self._evaluate_model(test_loader)
         # epochs exhausted before the PS stopped: keep answering until STOP

@@ -58,6 +58,8 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     p.add_argument("--weight-decay", type=float, default=0.0)
     p.add_argument("--nesterov", type=bool_flag, default=False)
     p.add_argument("--resume", type=bool_flag, default=False)
+    p.add_argument("--metrics-file", type=str, default="",
+                   help="also write every logged step as one JSON object per line to <path>.rank<R>.jsonl")
     p.add_argument("--max-restarts", type=int, default=0,
                    help="--nproc self-spawn: when the job fails (a rank died, the PS stopped it), relaunch it up to N "
                         "times from the latest checkpoint (--resume 1 is implied for the relaunches).  Under torchrun "

@@ -21,3 +21,29 @@ def master_line(step, decode_cost, lr, gather):
 
 def test_line(step, loss, prec1, prec5):
     return TEST_FMT.format(step, loss, prec1, prec5)
+
+
+class MetricsWriter:
+    """Machine-readable twin of the log lines (the reference has print() only): one JSON object per
+    line in ``<path>.rank<R>.jsonl`` — worker records carry the worker-line fields, PS records the PS-line fields plus
+    the aggregation bookkeeping.  ``path`` empty = disabled (every method is a no-op)."""
+
+    def __init__(self, path: str, rank: int, role: str):
+        import json
+        import time
+        self._json, self._time = json, time
+        self.rank, self.role = rank, role
+        self._f = open("%s.rank%d.jsonl" % (path, rank), "a") if path else None
+
+    def write(self, **fields):
+        if self._f is None:
+            return
+        rec = {"t": round(self._time.time(), 3), "role": self.role, "rank": self.rank}
+        rec.update({k: (float(v) if isinstance(v, float) else v) for k, v in fields.items()})
+        self._f.write(self._json.dumps(rec) + "\n")
+        self._f.flush()
+
+    def close(self):
+        if self._f is not None:
+            self._f.close()
+            self._f = None
