@@ -19,6 +19,16 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 
+class _HostEvent:
+    """perf_counter stand-in for torch.cuda.Event when the loop runs on a CPU stand-in engine (tests)."""
+
+    def record(self):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other) -> float:
+        return (other.t - self.t) * 1e3
+
+
 def _build_engine(args, model, rank, world):
     shadow = args.dtype == "bf16" and args.code.lower() in ("svd", "qsvd", "sgd", "dense", "lossless")
     if shadow:
@@ -41,7 +51,8 @@ def _build_engine(args, model, rank, world):
                        timeout_s=args.flag_timeout), "fused"
 
 
-def run_p2p_training(args):
+def run_p2p_training(args, device=None):
+    """``device`` is for the CPU tests of this loop (a stand-in engine on ``cpu``); real runs leave it None."""
     from ..data import DataLoader, build_datasets, shard_dataset
     from ..models import build_model
     from ..utils import checkpoint as ckpt
@@ -51,8 +62,10 @@ def run_p2p_training(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev = torch.device(device) if device is not None else torch.device("cuda", local_rank)
+    on_gpu = dev.type == "cuda"
+    if on_gpu:
+        torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", args.master_addr)
         os.environ.setdefault("MASTER_PORT", str(args.master_port))
@@ -84,13 +97,15 @@ def run_p2p_training(args):
         msg_mb = (eng.plan.expected_factor_bytes() + eng.plan.dense_bytes()) / 2 ** 20
     else:
         msg_mb = (eng.plan.factor_bytes_per_worker() + eng.plan.dense_bytes()) / 2 ** 20
-    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_a, ev_b = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if on_gpu else \
+        (_HostEvent(), _HostEvent())
     ev_a.record()
     since = 0
     eng.phase_stats(reset=True)
 
     def collective_barrier():
-        torch.cuda.synchronize(dev)
+        if on_gpu:
+            torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
 
