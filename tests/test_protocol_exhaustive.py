@@ -148,3 +148,124 @@ def test_stream_order_between_own_push_and_ps_launch_is_not_load_bearing():
     can possibly be there)."""
     res = explore(2, 2, [0, 1], 2, bug="no_stream_order")
     assert res["error"] is None and res["replicas_identical"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backup workers (--num-aggregate N < W): data-dependent control flow (skip-ahead, aggregation mask), so the
+# processes are small state machines instead of straight-line programs
+# ---------------------------------------------------------------------------------------------------------
+def explore_backup(W, G, owners, T, need, limit=3_000_000, bug=None):
+    """Owner: waits until `need` workers pushed group g of its step, picks ANY `need` of the ready ones (every choice
+    is explored), checks their slot stamps, updates, publishes.  Worker: waits for every owner's parameter flag,
+    skips ahead to min(flag) (a straggler that was left out does not replay old steps), pushes every group to every
+    owner.  Weights may be read while they change (inherent to in-place updates with backup workers), so only
+    deadlock-freedom, slot stamps and 'a worker is never ahead of an owner' are checked."""
+    from itertools import combinations
+    nO = len(owners)
+    keys, mem0 = [], {}
+    for r in range(W):
+        for o in range(nO):
+            mem0[("pf", r, o)] = 1
+    for o in range(nO):
+        for g in range(G):
+            for w in range(W):
+                mem0[("push", o, g, w)] = 0
+                mem0[("slot", o, g, w)] = 0
+    keys = sorted(mem0)
+    kidx = {k: i for i, k in enumerate(keys)}
+
+    def get(vals, k):
+        return vals[kidx[k]]
+
+    def put(vals, k, v):
+        i = kidx[k]
+        return vals[:i] + (v,) + vals[i + 1:]
+
+    def worker_moves(w, loc, vals):
+        t, phase, g, o = loc
+        if phase == "done":
+            return None
+        if phase == "wait":
+            flags = [get(vals, ("pf", w, x)) for x in range(nO)]
+            if min(flags) < t:
+                return []
+            t2 = t if bug == "no_skip_ahead" else min(flags)
+            return [((t2, "done", 0, 0), vals, None)] if t2 > T else [((t2, "slot", 0, 0), vals, None)]
+        if phase == "slot":
+            nv = put(vals, ("slot", o, g, w), t)
+            return [((t, "slot", g, o + 1) if o + 1 < nO else (t, "flag", g, 0), nv, None)]
+        nv = put(vals, ("push", o, g, w), t)                      # phase == "flag"
+        if o + 1 < nO:
+            return [((t, "flag", g, o + 1), nv, None)]
+        if g + 1 < G:
+            return [((t, "slot", g + 1, 0), nv, None)]
+        return [((t + 1, "done", 0, 0) if t + 1 > T else (t + 1, "wait", 0, 0), nv, None)]
+
+    def owner_moves(oi, loc, vals):
+        t, phase, g, i, mask = loc
+        if phase == "done":
+            return None
+        if phase == "waitpush":
+            ready = [w for w in range(W) if get(vals, ("push", oi, g, w)) >= t]
+            ahead = [w for w in ready if get(vals, ("push", oi, g, w)) > t]
+            if ahead:
+                return [(loc, vals, "a worker is ahead of an owner")]
+            if len(ready) < need:
+                return []
+            return [((t, "check", g, 0, m), vals, None) for m in combinations(ready, need)]
+        if phase == "check":
+            if get(vals, ("slot", oi, g, mask[i])) != t:
+                return [(loc, vals, "owner consumed a slot of another step")]
+            if i + 1 < need:
+                return [((t, "check", g, i + 1, mask), vals, None)]
+            return [((t, "waitpush", g + 1, 0, ()), vals, None)] if g + 1 < G else [((t, "publish", 0, 0, ()), vals, None)]
+        nv = put(vals, ("pf", i, oi), t + 1)                       # phase == "publish", i = rank
+        if i + 1 < W:
+            return [((t, "publish", 0, i + 1, ()), nv, None)]
+        return [((t + 1, "done", 0, 0, ()) if t + 1 > T else (t + 1, "waitpush", 0, 0, ()), nv, None)]
+
+    start = (tuple([(1, "wait", 0, 0)] * W + [(1, "waitpush", 0, 0, ())] * nO), tuple(mem0[k] for k in keys))
+    seen, todo = {start}, deque([start])
+    while todo:
+        locs, vals = todo.popleft()
+        moved, running = False, False
+        for p, loc in enumerate(locs):
+            moves = worker_moves(p, loc, vals) if p < W else owner_moves(p - W, loc, vals)
+            if moves is None:
+                continue
+            running = True
+            for nloc, nvals, err in moves:
+                if err:
+                    return {"error": err, "states": len(seen)}
+                moved = True
+                nxt = (locs[:p] + (nloc,) + locs[p + 1:], nvals)
+                if nxt not in seen:
+                    seen.add(nxt)
+                    todo.append(nxt)
+                    if len(seen) > limit:
+                        return {"error": "state space larger than %d" % limit, "states": len(seen)}
+        if running and not moved:
+            return {"error": "deadlock", "states": len(seen), "at": locs}
+    return {"error": None, "states": len(seen)}
+
+
+@pytest.mark.parametrize("W,G,owners,T,need", [
+    (3, 1, [0], 3, 2),        # centralized PS, 2 of 3
+    (3, 2, [0], 2, 2),        # two backward groups: the mask may differ per group
+    (2, 1, [0, 1], 3, 1),     # sharded PS, 1 of 2: owners themselves can be the stragglers
+    (3, 1, [0, 1], 2, 2),     # sharded over two owners, 2 of 3
+    (3, 2, [0, 1], 2, 2),     # ... with two backward groups (118 k states)
+    (4, 1, [0], 2, 3),        # 3 of 4
+])
+def test_backup_worker_protocol_every_interleaving(W, G, owners, T, need):
+    res = explore_backup(W, G, owners, T, need)
+    assert res["error"] is None, res
+    assert res["states"] > 100
+
+
+def test_skip_ahead_is_an_optimisation_not_a_safety_requirement():
+    """A straggler that replays the steps it missed (no skip-ahead) pushes flags that are too old to be used and
+    eventually catches up or finishes: still no deadlock and no slot of another step consumed.  Skipping ahead only
+    saves it the wasted work."""
+    res = explore_backup(3, 1, [0], 3, 2, bug="no_skip_ahead")
+    assert res["error"] is None, res
