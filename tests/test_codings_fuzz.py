@@ -4,6 +4,8 @@ deterministic coders must be exact."""
 import numpy as np
 import pytest
 import torch
+import pytest as _pytest
+_pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings, strategies as st
 
 from atomo_b200 import codings

@@ -4,6 +4,8 @@ import os
 
 import pytest
 import torch
+import pytest as _pytest
+_pytest.importorskip("hypothesis")
 from hypothesis import given, settings, strategies as st
 
 from atomo_b200.data import DataLoader, shard_indices

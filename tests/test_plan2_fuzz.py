@@ -4,6 +4,8 @@ slot / Gram-partial / staging region must lie inside its buffer without overlapp
 the kernels' shared-memory and register-tile limits."""
 import numpy as np
 import pytest
+import pytest as _pytest
+_pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings, strategies as st
 
 from atomo_b200.ops import plan2 as P

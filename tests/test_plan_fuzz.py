@@ -1,6 +1,8 @@
 """Property tests of the fp32-flat engine's planner (ops/plan.py), same purpose as tests/test_plan2_fuzz.py: the
 kernels of csrc/{svd,ps,ext}_kernels.cu trust these tables blindly."""
 import numpy as np
+import pytest as _pytest
+_pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings, strategies as st
 
 from atomo_b200.ops import plan as P
