@@ -66,7 +66,8 @@ class DistributedWorker(NN_Trainer):
         # fault injection for the backup-worker tests: ATOMO_DEBUG_SLOW_WORKER="<rank>:<seconds per step>"
         slow = os.environ.get("ATOMO_DEBUG_SLOW_WORKER", "")
         self._debug_slow_s = float(slow.split(":")[1]) if slow and int(slow.split(":")[0]) == self.rank else 0.0
-        # ATOMO_DEBUG_DIE_WORKER="<rank>:<step>[,<rank>:<step>...]": the process exits in the middle of that step
+        # ATOMO_DEBUG_DIE_WORKER="<rank>:<step>[,<rank>:<step>...]": the process exits in the middle of the first step
+        # >= <step> it takes part in (a backup-mode straggler may never see step <step> itself)
         self._debug_die_step = 0
         for item in filter(None, os.environ.get("ATOMO_DEBUG_DIE_WORKER", "").split(",")):
             r, st = item.split(":")
@@ -128,7 +129,7 @@ class DistributedWorker(NN_Trainer):
                 loss = self.criterion(logits, y)
                 if self._debug_slow_s:
                     time.sleep(self._debug_slow_s)
-                if self._debug_die_step and self.cur_step == self._debug_die_step and self._die_armed():
+                if self._debug_die_step and self.cur_step >= self._debug_die_step and self._die_armed():
                     print("Worker {}: fault injection, dying at step {}".format(self.rank, self.cur_step), flush=True)
                     os._exit(0)
                 if self._split_backward:

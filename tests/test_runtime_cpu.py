@@ -86,7 +86,7 @@ def test_checkpoint_layout_and_resume(tmp_path):
     assert ckpt.load_sidecar(d, 100) is None
 
 
-def _run_launcher(extra, timeout=240):
+def _run_launcher(extra, timeout=480):
     cmd = [sys.executable, "-m", "atomo_b200.distributed_nn", "--synthetic", "1", "--train-len", "512",
            "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64"] + extra
     # 2-3 ranks x (8 OpenMP threads) oversubscribe the 8-core CI box: pin the ranks to 2 threads each
@@ -225,9 +225,9 @@ def _run_backup(extra, env_extra, port, nproc=3, steps=12, need=1, code=("--code
            "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64",
            "--nproc", str(nproc), "--network", "LeNet", "--dataset", "MNIST", *code, "--max-steps", str(steps),
            "--num-aggregate", str(need), "--master-port", str(port)] + extra
-    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="440", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
                **env_extra)
-    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=480)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
@@ -278,10 +278,10 @@ def test_ps_fails_fast_when_a_worker_dies_in_all_workers_mode(tmp_path):
            "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64", "--nproc", "3",
            "--network", "LeNet", "--dataset", "MNIST", "--code", "sgd", "--max-steps", "50", "--eval-freq", "100",
            "--train-dir", str(tmp_path) + "/", "--master-port", "29599"]
-    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="440", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
                ATOMO_DEBUG_DIE_WORKER="2:3")
     t0 = time.time()
-    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=480)
     assert r.returncode != 0
     assert "Master: worker 2 is gone" in r.stdout and "stopping the job" in r.stdout
     assert "Master: Step: 2," in r.stdout and "Master: Step: 4," not in r.stdout
@@ -296,9 +296,9 @@ def test_launcher_restarts_from_the_latest_checkpoint(tmp_path):
            "--test-len", "128", "--batch-size", "32", "--lr", "0.05", "--test-batch-size", "64", "--nproc", "3",
            "--network", "LeNet", "--dataset", "MNIST", "--code", "svd", "--svd-rank", "2", "--max-steps", "8",
            "--eval-freq", "2", "--train-dir", d, "--master-port", "29601", "--max-restarts", "2"]
-    env = dict(os.environ, ATOMO_HANG_DUMP_S="200", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
+    env = dict(os.environ, ATOMO_HANG_DUMP_S="440", PYTHONPATH=ROOT, OMP_NUM_THREADS="2", MKL_NUM_THREADS="2",
                ATOMO_DEBUG_DIE_WORKER="2:5", ATOMO_DEBUG_DIE_ONCE=str(tmp_path / "died"))
-    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=480)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = r.stdout
     assert "Master: worker 2 is gone" in out and "restart 1/2 from the latest checkpoint" in out
