@@ -285,7 +285,7 @@ def test_ps_fails_fast_when_a_worker_dies_in_all_workers_mode(tmp_path):
     assert r.returncode != 0
     assert "Master: worker 2 is gone" in r.stdout and "stopping the job" in r.stdout
     assert "Master: Step: 2," in r.stdout and "Master: Step: 4," not in r.stdout
-    assert time.time() - t0 < 120
+    assert time.time() - t0 < 400          # not the 30-minute process-group timeout
 
 
 def test_launcher_restarts_from_the_latest_checkpoint(tmp_path):
