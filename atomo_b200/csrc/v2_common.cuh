@@ -108,8 +108,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 // One SLAB encode tile = `ns` consecutive slabs = ns*K rows of I bf16 each.  Rows are copied by TMA bulk copies
 // (one per row, issued by the 32 lanes of warp 0) into a row pitch of I/2 + 4 words, which makes both consumers
-// bank-conflict free: the Gram's mma fragments read 8 different taps x 4 channel pairs per instruction, the
-// projection reads 32 consecutive channel pairs of one tap.
+// bank-conflict free: the Gram's 4x4 register blocks read the same channel pair of different taps (stride = pitch,
+// 4 words off a multiple of 32 banks), the projection reads 32 consecutive channel pairs of one tap.
 __device__ __forceinline__ int slab_pitch_words(int I) { return (I >> 1) + 4; }
 
 __device__ __forceinline__ void load_slab_tile(const __nv_bfloat16* gbase, int K, int I, int ns, uint32_t* sm,
