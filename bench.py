@@ -343,7 +343,7 @@ def fp32_child(args, rank, world):
            "--batch-size", str(args.batch_size), "--code", args.code, "--svd-rank", str(args.svd_rank), "--dataset",
            args.dataset, "--momentum", str(args.momentum), "--lr", str(args.lr)]
     try:
-        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
     except Exception as e:  # noqa
         return {"unavailable": "fp32 child failed: %r" % (e,)}
     if rank != 0:
