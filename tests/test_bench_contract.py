@@ -77,3 +77,18 @@ def test_clock_sampler_shape_without_a_gpu():
     s.start()
     out = s.stop()
     assert set(out) == {"sm_mhz", "sm_max_mhz", "reasons"} and isinstance(out["reasons"], list)
+
+
+def test_built_extension_is_the_profiled_one():
+    """Evidence integrity: every kernel of the built extension is instruction-identical to its committed SASS listing
+    (profiles/sass/, taken from the build that ran the GPU tests, benches and ncu captures).  Skipped when the
+    extension has not been built yet or cuobjdump is not on PATH."""
+    import glob
+    import shutil
+    import pytest
+    if not glob.glob(os.path.join(ROOT, "atomo_b200", "_C*.so")) or shutil.which("cuobjdump") is None:
+        pytest.skip("needs the built extension and cuobjdump")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_sass_listings.py")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:]
+    assert r.stdout.count("identical") >= 27
