@@ -99,3 +99,34 @@ def test_split_kill_variants():
     assert sm.backward_timeout_kill(loss, timeout_s=-1.0) is True
     loss = sm.criterion(sm(x), y)
     sm.backward_single(loss)
+
+
+def test_sidecar_restores_the_full_adam_state(tmp_path):
+    """--resume on the role path: the `_optim` sidecar carries the optimizer's whole state (Adam moments, step
+    counts), so a resumed PS takes exactly the step the uninterrupted one would have taken."""
+    from atomo_b200.optim import Adam
+    from atomo_b200.utils import checkpoint as ckpt
+    torch.manual_seed(0)
+    d = str(tmp_path) + "/"
+
+    def make():
+        torch.manual_seed(1)
+        net = torch.nn.Linear(6, 3)
+        return net, Adam(net.parameters(), lr=0.01, amsgrad=True)
+
+    grads = [[torch.randn(3, 6), torch.randn(3)] for _ in range(5)]
+    a, oa = make()
+    for g in grads[:3]:
+        oa.step(grads=g)
+    ckpt.save_model(d, 3, a)
+    ckpt.save_sidecar(d, 3, oa, lr=0.01)
+    for g in grads[3:]:
+        oa.step(grads=g)
+    b, ob = make()
+    ckpt.load_model(d, 3, b)
+    side = ckpt.load_sidecar(d, 3, ob)
+    assert side["step"] == 3 and side["lr"] == 0.01
+    for g in grads[3:]:
+        ob.step(grads=g)
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, atol=1e-7)
