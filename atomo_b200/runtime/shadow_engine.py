@@ -540,7 +540,8 @@ class ShadowEngine:
 
     def save_checkpoint(self, train_dir: str, step: Optional[int] = None) -> Optional[str]:
         """Collective.  The first training rank writes ``model_step_<N>`` (fp32, trained BN statistics) and the
-        ``_optim`` sidecar (momentum, step, LR) so a later run can resume."""
+        ``_optim`` sidecar (momentum — for Adam / AMSGrad also the second moments —, step, LR) so a later run can
+        resume."""
         from ..utils import checkpoint as ckpt
         step = (self.step - 1) if step is None else step
         sd = self.fp32_state_dict()
@@ -550,6 +551,15 @@ class ShadowEngine:
         vm = vmom * mv
         if self.world > 1:
             dist.all_reduce(vm, group=self.group)
+        adam_state = {}
+        if self.opt != P2.OPT_SGD:      # Adam / AMSGrad: second moments too (collective gathers, every rank takes part)
+            names = [("sq", "vsq")] + ([("sqmax", "vsqmax")] if self.opt == P2.OPT_AMSGRAD else [])
+            for wname, vname in names:
+                vt = (getattr(self, vname) if self.is_owner else torch.zeros_like(self.vparams)) * mv
+                if self.world > 1:
+                    dist.all_reduce(vt, group=self.group)
+                adam_state[wname + "_w"] = self.gather_fp32(wname).cpu()
+                adam_state[wname + "_v"] = vt.cpu()
         if self.rank != self.first_worker:
             return None
         path = ckpt.model_path(train_dir, step)
@@ -559,6 +569,7 @@ class ShadowEngine:
         os.replace(tmp, path)
         side = {"step": step, "lr": self.lr, "mom_w": mom.cpu(), "mom_v": vm.cpu(), "code": self.code,
                 "svd_rank": self.svd_rank, "engine": "shadow"}
+        side.update(adam_state)
         torch.save(side, path + "_optim.tmp")
         os.replace(path + "_optim.tmp", path + "_optim")
         return path
@@ -592,6 +603,10 @@ class ShadowEngine:
                 if "mom_w" in side:
                     self.mom.copy_(side["mom_w"].to(self.device))
                     self.vmom.copy_(side["mom_v"].to(self.device))
+                for wname, vname in (("sq", "vsq"), ("sqmax", "vsqmax")):      # Adam / AMSGrad second moments
+                    if wname + "_w" in side and getattr(self, wname, None) is not None:
+                        getattr(self, wname).copy_(side[wname + "_w"].to(self.device))
+                        getattr(self, vname).copy_(side[vname[1:] + "_v"].to(self.device))
                 if side.get("lr") is not None:
                     self.set_lr(float(side["lr"]))
         self.step = step + 1
