@@ -59,8 +59,17 @@ def _tall(grad: torch.Tensor) -> Tuple[torch.Tensor, bool]:
 class BlockSVD(Coding):
     def __init__(self, rank: int = 3, random_sample: bool = True, prob_rule: str = "reference",
                  scheme: str = "bernoulli", block_cols: int = 32, generator: Optional[torch.Generator] = None,
-                 *args, **kwargs):
+                 allocation: str = "per_block", *args, **kwargs):
+        """``allocation="per_block"`` is what the sm_100a engine does today (every block samples with its own budget
+        ``ceil(rank / blocks)``).  ``"global"`` treats the atoms of ALL blocks of a tensor as one atom set with
+        ``p_i = min(1, rank * sigma_i / sum_all sigma)`` — ATOMO's optimal allocation for this decomposition, ``rank``
+        expected atoms per tensor instead of per block; still unbiased (any probabilities are).  It needs one number
+        per tensor shared by its blocks, which the fused kernel could take from the previous step; evaluated here on
+        CPU first (``docs/experiments/variance_*.md``)."""
         super().__init__()
+        if allocation not in ("per_block", "global"):
+            raise ValueError("allocation: per_block | global")
+        self.allocation = allocation
         self.svd_rank = max(int(rank), 1)
         self.random_sample = random_sample
         self.prob_rule = prob_rule
@@ -69,15 +78,19 @@ class BlockSVD(Coding):
         self.generator = generator
 
     # ------------------------------------------------------------------
-    def _code_unit(self, a: torch.Tensor, budget: float):
-        """One unit ``a`` (rows x cols, fp32): Gram -> eigenvectors -> sampled atoms ``(U, s/p, V^T)``."""
+    def _code_unit(self, a: torch.Tensor, budget: float, total_sigma: Optional[float] = None):
+        """One unit ``a`` (rows x cols, fp32): Gram -> eigenvectors -> sampled atoms ``(U, s/p, V^T)``.
+        ``total_sigma`` (global allocation): nuclear-norm normaliser shared by all blocks of the tensor."""
         lam, v = torch.linalg.eigh(a.t() @ a)
         lam, v = lam.flip(0).clamp_min(0), v.flip(1)
         sigma = lam.sqrt()
         if float(sigma[0]) < 1e-12:
             return a.new_zeros(a.shape[0], 0), a.new_zeros(0), a.new_zeros(0, a.shape[1])
         if self.random_sample:
-            p = atom_probabilities(sigma, budget, self.prob_rule)
+            if total_sigma is not None:
+                p = (budget * sigma / total_sigma).clamp(max=1.0)
+            else:
+                p = atom_probabilities(sigma, budget, self.prob_rule)
             idx = sample_atoms(p, scheme=self.scheme, generator=self.generator, allow_empty=True)
             idx = idx[sigma[idx] > 1e-12 * sigma[0]]
             scale = 1.0 / p[idx].to(sigma.dtype)
@@ -101,8 +114,14 @@ class BlockSVD(Coding):
             units.append({"u": u, "s": s, "vT": vT})
         else:
             tall, _ = _tall(g)
+            total = None
+            if self.allocation == "global" and self.random_sample and len(table) > 1:
+                total = float(sum(torch.linalg.svdvals(tall[:, c0:c0 + cols]).sum() for _, _, cols, c0, _ in table))
             for _, rows, cols, c0, budget in table:
-                u, s, vT = self._code_unit(tall[:, c0:c0 + cols], budget)
+                if total is not None:
+                    u, s, vT = self._code_unit(tall[:, c0:c0 + cols], float(self.svd_rank), max(total, 1e-30))
+                else:
+                    u, s, vT = self._code_unit(tall[:, c0:c0 + cols], budget)
                 units.append({"u": u, "s": s, "vT": vT})
         return {"units": units, "orig_size": list(g.shape), "encode": True, "rank": self.svd_rank,
                 "block_cols": self.block_cols}
