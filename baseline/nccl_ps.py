@@ -51,8 +51,9 @@ def run_baseline(args, rank, world, dev):
     is_worker = world == 1 or rank > 0
     nworkers = max(world - 1, 1)
     code = args.code if args.code != "sgd" else "sgd"
-    enc = codings.build(code, rank=args.svd_rank, random_sample=True) if code == "svd" else codings.build(code)
-    dec = codings.build(code, rank=args.svd_rank, random_sample=False) if code == "svd" else codings.build(code)
+    # gram_route=False: the comparator stays what BASELINE.md names, torch.linalg.svd per tensor
+    enc = codings.build(code, rank=args.svd_rank, random_sample=True, gram_route=False) if code == "svd" else codings.build(code)
+    dec = codings.build(code, rank=args.svd_rank, random_sample=False, gram_route=False) if code == "svd" else codings.build(code)
     opt = SGD(model.parameters(), lr=args.lr, momentum=args.momentum) if is_ps else None
     shape = input_shape(args.network, "Cifar10")
     xs, ys = SyntheticImageDataset(shape, 10, 50000, seed=rank).materialize(args.batch_size)

@@ -192,3 +192,34 @@ def test_wire_roundtrip_property():
             assert torch.equal(c["t"], t) and c["shape"] == list(t.shape) and c["tag"] == "x"
 
     check()
+
+
+@pytest.mark.parametrize("shape", [(4096, 18), (18, 4096), (2048, 50), (300, 64), (40, 40), (1000, 3), (7, 1)])
+def test_gram_route_matches_lapack(shape):
+    """svd coder fast path: tall-skinny (and short-fat) matrices are factorized through the Gram matrix of the small
+    side.  Same singular values as LAPACK, exact reconstruction, orthonormal factors; square-ish ones still use LAPACK."""
+    from atomo_b200.codings.svd import thin_svd
+    a = torch.randn(shape, generator=torch.Generator().manual_seed(5))
+    u, s, vT = thin_svd(a, True)
+    ur, sr, vr = torch.linalg.svd(a, full_matrices=False)
+    assert u.shape == ur.shape and vT.shape == vr.shape
+    assert torch.allclose(s, sr, rtol=2e-5, atol=1e-6)
+    assert torch.allclose((u * s) @ vT, a, atol=2e-5 * float(sr[0]))
+    k = s.numel()
+    assert torch.allclose(u.t() @ u, torch.eye(k), atol=2e-4) and torch.allclose(vT @ vT.t(), torch.eye(k), atol=2e-4)
+
+
+def test_gram_route_survives_rank_deficiency_and_keeps_atoms_exact():
+    from atomo_b200.codings.svd import thin_svd
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(3000, 4, generator=g) @ torch.randn(4, 18, generator=g)      # rank 4 of 18
+    a[:, 7] = 0
+    u, s, vT = thin_svd(a, True)
+    assert torch.isfinite(u).all() and torch.isfinite(s).all() and float(s[4]) < 1e-3 * float(s[0])
+    assert torch.allclose((u * s) @ vT, a, atol=1e-4 * float(s[0]))             # u_i s_i = A v_i whatever sigma_i is
+    z = thin_svd(torch.zeros(500, 6), True)
+    assert all(torch.isfinite(t).all() for t in z) and float(z[1].abs().max()) == 0.0
+    coder = codings.build("svd", rank=3, random_sample=False)
+    ref = codings.build("svd", rank=3, random_sample=False, gram_route=False)
+    x = torch.randn(64, 32, 3, 3, generator=g)
+    assert torch.allclose(coder.decode(coder.encode(x)), ref.decode(ref.encode(x)), atol=1e-4)
